@@ -1,0 +1,55 @@
+// Shared host/device helpers for libfemasr_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "femasr_b200.h"
+
+namespace femasr {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+// global launch counter (incremented by every kernel launch helper); read by the engine
+extern thread_local long g_launches;
+
+#define FEMASR_CHECK_ARG(cond, msg)                                           \
+  do {                                                                        \
+    if (!(cond)) return ::femasr::fail(FEMASR_ERR_ARG, std::string(msg));     \
+  } while (0)
+
+#define FEMASR_CUDA(call)                                                                       \
+  do {                                                                                          \
+    cudaError_t _e = (call);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return ::femasr::fail(FEMASR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+inline int launch_status(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  ++g_launches;
+  if (e != cudaSuccess) return fail(FEMASR_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return FEMASR_OK;
+}
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__host__ __device__ inline long cdiv(long a, long b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+// exact-erf GELU (nn.GELU default; SURVEY 7.3-7: tanh approximation breaks parity)
+__device__ __forceinline__ float gelu_erf_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace femasr

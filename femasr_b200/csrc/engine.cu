@@ -1,0 +1,536 @@
+// Host-side engine: the FeMaSRNet inference graph (femasr_arch.py:311-385) as a fixed kernel sequence
+// over a caller-provided device workspace.  No arithmetic happens here; every step is one of the
+// exported operator kernels.  The graph is data-independent, so one forward = one launch list that a
+// caller may capture in a CUDA graph.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace femasr {
+
+static thread_local std::string g_err;
+thread_local long g_launches = 0;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+// ---------------------------------------------------------------------------------------------
+// Offset allocator over the workspace (first fit + coalescing).  Deterministic, so a dry run with
+// base == nullptr yields the exact high-water mark the real run needs.
+struct Arena {
+  struct Blk { size_t off, size; bool free; };
+  std::vector<Blk> blks;
+  char* base = nullptr;
+  size_t top = 0, peak = 0, cap = 0;
+  bool dry = true;
+  static size_t align(size_t n) { return (n + 255) & ~size_t(255); }
+  size_t alloc_off(size_t bytes) {
+    bytes = align(std::max<size_t>(bytes, 256));
+    for (size_t i = 0; i < blks.size(); ++i) {
+      if (blks[i].free && blks[i].size >= bytes) {
+        if (blks[i].size > bytes) {
+          Blk rest{blks[i].off + bytes, blks[i].size - bytes, true};
+          blks[i].size = bytes;
+          blks.insert(blks.begin() + i + 1, rest);
+        }
+        blks[i].free = false;
+        return blks[i].off;
+      }
+    }
+    Blk b{top, bytes, false};
+    blks.push_back(b);
+    top += bytes;
+    peak = std::max(peak, top);
+    return b.off;
+  }
+  float* alloc(size_t nfloats) {
+    size_t off = alloc_off(nfloats * sizeof(float));
+    return reinterpret_cast<float*>(base + off);   // only dereferenced when !dry
+  }
+  void release(const void* p) {
+    size_t off = (size_t)(reinterpret_cast<const char*>(p) - base);
+    for (size_t i = 0; i < blks.size(); ++i) {
+      if (blks[i].off == off && !blks[i].free) {
+        blks[i].free = true;
+        if (i + 1 < blks.size() && blks[i + 1].free) { blks[i].size += blks[i + 1].size; blks.erase(blks.begin() + i + 1); }
+        if (i > 0 && blks[i - 1].free) { blks[i - 1].size += blks[i].size; blks.erase(blks.begin() + i); }
+        while (!blks.empty() && blks.back().free) { top = blks.back().off; blks.pop_back(); }
+        return;
+      }
+    }
+  }
+};
+
+struct DevBuf {
+  float* p = nullptr;
+  size_t n = 0;
+};
+
+struct ParamInfo {
+  size_t numel;
+  int kind;  // 0 plain, 1 conv/linear weight [Cout,Cin,k,k], 2 rel-pos table, 3 codebook
+  int Cout, Cin, k;
+};
+
+struct Tap { float* dst; size_t cap; };
+
+}  // namespace femasr
+
+using namespace femasr;
+
+struct femasr_net {
+  femasr_net_config cfg;
+  int depth;   // encode depth (1 for x4, 2 for x2)
+  std::map<std::string, ParamInfo> spec;
+  std::map<std::string, DevBuf> raw;      // fp32 copy in the reference layout
+  std::map<std::string, DevBuf> packed;   // K-major GEMM operand / expanded rel bias / codebook^T
+  std::map<std::string, DevBuf> tcw;      // tensor-core operand (split fp16), gemm_path 1
+  DevBuf esq;
+  std::map<std::string, Tap> taps;
+  int last_launches = 0;
+  ~femasr_net() {
+    for (auto& kv : raw) cudaFree(kv.second.p);
+    for (auto& kv : packed) cudaFree(kv.second.p);
+    for (auto& kv : tcw) cudaFree(kv.second.p);
+    cudaFree(esq.p);
+  }
+};
+
+namespace femasr {
+
+static int chan(int res) {
+  switch (res) { case 8: case 16: case 32: case 64: return 256; case 128: return 128; case 256: return 64; case 512: return 32; }
+  return -1;
+}
+
+static void add_conv(femasr_net* n, const std::string& p, int ci, int co, int k) {
+  n->spec[p + ".weight"] = ParamInfo{(size_t)co * ci * k * k, 1, co, ci, k};
+  n->spec[p + ".bias"] = ParamInfo{(size_t)co, 0, 0, 0, 0};
+}
+static void add_vec(femasr_net* n, const std::string& name, size_t c) { n->spec[name] = ParamInfo{c, 0, 0, 0, 0}; }
+static void add_resblock(femasr_net* n, const std::string& p, int c) {
+  add_vec(n, p + ".conv.0.norm.weight", c); add_vec(n, p + ".conv.0.norm.bias", c);
+  add_conv(n, p + ".conv.2", c, c, 3);
+  add_vec(n, p + ".conv.3.norm.weight", c); add_vec(n, p + ".conv.3.norm.bias", c);
+  add_conv(n, p + ".conv.5", c, c, 3);
+}
+
+static void build_spec(femasr_net* n) {
+  const int scale = n->cfg.scale_factor, e = n->cfg.e_dim;
+  const int d = n->depth;
+  int res = 256 / scale;
+  const std::string enc = "multiscale_encoder";
+  add_conv(n, enc + ".in_conv", n->cfg.in_channel, chan(res), 4);
+  for (int i = 0; i < d; ++i) {
+    const std::string b = enc + ".blocks." + std::to_string(i);
+    add_conv(n, b + ".0", chan(res), chan(res / 2), 3);
+    add_resblock(n, b + ".1", chan(res / 2));
+    add_resblock(n, b + ".2", chan(res / 2));
+    res /= 2;
+  }
+  const std::string sw = enc + ".blocks." + std::to_string(d) + ".swin_blks.";
+  for (int r = 0; r < 4; ++r) {
+    for (int b = 0; b < 6; ++b) {
+      const std::string p = sw + std::to_string(r) + ".residual_group.blocks." + std::to_string(b);
+      add_vec(n, p + ".norm1.weight", 256); add_vec(n, p + ".norm1.bias", 256);
+      n->spec[p + ".attn.relative_position_bias_table"] = ParamInfo{225 * 8, 2, 0, 0, 0};
+      add_conv(n, p + ".attn.qkv", 256, 768, 1);
+      add_conv(n, p + ".attn.proj", 256, 256, 1);
+      add_vec(n, p + ".norm2.weight", 256); add_vec(n, p + ".norm2.bias", 256);
+      add_conv(n, p + ".mlp.fc1", 256, 1024, 1);
+      add_conv(n, p + ".mlp.fc2", 1024, 256, 1);
+    }
+    add_conv(n, sw + std::to_string(r) + ".conv", 256, 256, 3);
+  }
+  for (int j = d + 1; j <= d + 2; ++j) {
+    const std::string b = enc + ".blocks." + std::to_string(j);
+    add_conv(n, b + ".1", chan(res), chan(res * 2), 3);
+    add_resblock(n, b + ".2", chan(res * 2));
+    add_resblock(n, b + ".3", chan(res * 2));
+    res *= 2;
+  }
+  for (int i = 0; i < 3; ++i) {
+    const int r = 32 << i;
+    const std::string b = "decoder_group." + std::to_string(i) + ".block";
+    add_conv(n, b + ".1", chan(r), chan(r * 2), 3);
+    add_resblock(n, b + ".2", chan(r * 2));
+    add_resblock(n, b + ".3", chan(r * 2));
+  }
+  add_conv(n, "out_conv", 64, 3, 3);
+  n->spec["quantize_group.0.embedding.weight"] = ParamInfo{(size_t)n->cfg.n_e * e, 3, n->cfg.n_e, e, 1};
+  add_conv(n, "before_quant_group.0", 256, e, 1);
+  add_conv(n, "after_quant_group.0.conv", e, 256, 3);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Ctx {
+  femasr_net* net;
+  Arena ar;
+  cudaStream_t st;
+  int status = FEMASR_OK;
+  bool dry() const { return ar.dry; }
+  bool ok() const { return status == FEMASR_OK; }
+  void check(int s) { if (status == FEMASR_OK && s != FEMASR_OK) status = s; }
+
+  const float* P(const std::string& name) {      // packed (or raw when there is no packed form)
+    if (dry()) return nullptr;
+    auto it = net->packed.find(name);
+    if (it != net->packed.end()) return it->second.p;
+    auto jt = net->raw.find(name);
+    if (jt == net->raw.end()) { check(fail(FEMASR_ERR_STATE, "parameter not set: " + name)); return nullptr; }
+    return jt->second.p;
+  }
+  const void* TCW(const std::string& name) {
+    auto it = net->tcw.find(name);
+    return it == net->tcw.end() ? nullptr : it->second.p;
+  }
+  void tap(const char* stage, const float* src, size_t n) {
+    if (dry() || !ok()) return;
+    auto it = net->taps.find(stage);
+    if (it == net->taps.end() || !it->second.dst) return;
+    if (it->second.cap < n) { check(fail(FEMASR_ERR_ARG, std::string("tap buffer too small: ") + stage)); return; }
+    cudaError_t e = cudaMemcpyAsync(it->second.dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) check(fail(FEMASR_ERR_CUDA, cudaGetErrorString(e)));
+  }
+
+  // y = conv(x) (+epilogue); wname is the conv's parameter prefix.
+  void conv(const std::string& wname, const float* x, float* y, int B, int Hin, int Win, int Cin, int Cout, int ksize,
+            int stride, int upsample, int prologue, const float* pa, const float* pb, const float* gamma,
+            const float* beta, int act, const float* res1, const float* res2, bool has_bias = true) {
+    if (dry() || !ok()) return;
+    femasr_igemm_args a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.w = P(wname + ".weight"); a.bias = has_bias ? P(wname + ".bias") : nullptr;
+    a.res1 = res1; a.res2 = res2; a.y = y; a.pro_a = pa; a.pro_b = pb; a.gamma = gamma; a.beta = beta;
+    a.B = B; a.Hin = Hin; a.Win = Win; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.stride = stride;
+    a.upsample = upsample; a.prologue = prologue; a.act = act;
+    if (!ok()) return;
+    check(femasr_igemm_simt(&a, st));
+  }
+
+  // GroupNorm statistics of x folded into scale/shift tables (allocated by the caller)
+  void gn(const std::string& norm, const float* x, float* sc, float* sh, float* scratch, int B, int HW, int C) {
+    if (dry() || !ok()) return;
+    check(femasr_gn_stats(x, P(norm + ".weight"), P(norm + ".bias"), sc, sh, scratch, B, HW, C, 1e-6f, st));
+  }
+
+  // fema_utils.py:65-84, in place on x; optional extra residual added after the block (encoder skip).
+  void resblock(const std::string& p, float* x, int B, int H, int W, int C, const float* extra) {
+    const size_t n = (size_t)B * H * W * C;
+    float* sc = ar.alloc((size_t)B * C);
+    float* sh = ar.alloc((size_t)B * C);
+    float* scratch = ar.alloc(femasr_gn_scratch_floats(B, H * W, C));
+    float* t = ar.alloc(n);
+    gn(p + ".conv.0.norm", x, sc, sh, scratch, B, H * W, C);
+    conv(p + ".conv.2", x, t, B, H, W, C, C, 3, 1, 0, FEMASR_PRO_GN_SILU, sc, sh, nullptr, nullptr, 0, nullptr, nullptr);
+    gn(p + ".conv.3.norm", t, sc, sh, scratch, B, H * W, C);
+    conv(p + ".conv.5", t, x, B, H, W, C, C, 3, 1, 0, FEMASR_PRO_GN_SILU, sc, sh, nullptr, nullptr, 0, x, extra);
+    ar.release(t); ar.release(scratch); ar.release(sh); ar.release(sc);
+  }
+
+  // nn.Upsample(2) -> conv3x3 -> ResBlock -> ResBlock  (femasr_arch.py:168-180, 195-211); returns new buffer
+  float* up_block(const std::string& pconv, const std::string& prb1, const std::string& prb2, const float* x, int B,
+                  int H, int W, int Cin, int Cout, const float* extra) {
+    float* y = ar.alloc((size_t)B * 2 * H * 2 * W * Cout);
+    conv(pconv, x, y, B, H, W, Cin, Cout, 3, 1, 1, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
+    resblock(prb1, y, B, 2 * H, 2 * W, Cout, nullptr);
+    resblock(prb2, y, B, 2 * H, 2 * W, Cout, extra);
+    return y;
+  }
+
+  // SwinLayers (femasr_arch.py:126-132): 4 x RSTB on tokens X [B, H*W, 256], in place.
+  void swin(const std::string& p, float* X, int B, int H, int W) {
+    const int C = 256;
+    const size_t M = (size_t)B * H * W;
+    float* T = ar.alloc(M * C);
+    float* qkv = ar.alloc(M * 3 * C);
+    float* ao = ar.alloc(M * C);
+    float* hid = ar.alloc(M * 4 * C);
+    float* mu = ar.alloc(M);
+    float* rs = ar.alloc(M);
+    for (int r = 0; r < 4; ++r) {
+      const std::string rp = p + ".swin_blks." + std::to_string(r);
+      for (int b = 0; b < 6; ++b) {
+        const std::string bp = rp + ".residual_group.blocks." + std::to_string(b);
+        const float* in = b == 0 ? X : T;
+        if (!dry() && ok()) check(femasr_ln_stats(in, mu, rs, (int)M, C, 1e-5f, st));
+        conv(bp + ".attn.qkv", in, qkv, B, H, W, C, 3 * C, 1, 1, 0, FEMASR_PRO_LN, mu, rs, P(bp + ".norm1.weight"),
+             P(bp + ".norm1.bias"), 0, nullptr, nullptr);
+        if (!dry() && ok())
+          check(femasr_window_attention(qkv, P(bp + ".attn.relative_position_bias_table"), ao, B, H, W, C, 8,
+                                        (b & 1) ? 4 : 0, st));
+        conv(bp + ".attn.proj", ao, T, B, H, W, C, C, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, in, nullptr);
+        if (!dry() && ok()) check(femasr_ln_stats(T, mu, rs, (int)M, C, 1e-5f, st));
+        conv(bp + ".mlp.fc1", T, hid, B, H, W, C, 4 * C, 1, 1, 0, FEMASR_PRO_LN, mu, rs, P(bp + ".norm2.weight"),
+             P(bp + ".norm2.bias"), FEMASR_ACT_GELU, nullptr, nullptr);
+        conv(bp + ".mlp.fc2", hid, T, B, H, W, 4 * C, C, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, T, nullptr);
+      }
+      conv(rp + ".conv", T, X, B, H, W, C, C, 3, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, X, nullptr);
+    }
+    ar.release(rs); ar.release(mu); ar.release(hid); ar.release(ao); ar.release(qkv); ar.release(T);
+  }
+
+  // after_quant conv + 3 decoder blocks + out_conv.  x0in: [B,h,w,e] quantised features.
+  void decode(const float* zq, float* y_nchw, int B, int h, int w, const float* u1, const float* u2) {
+    const int e = net->cfg.e_dim;
+    float* x0 = ar.alloc((size_t)B * h * w * 256);
+    conv("after_quant_group.0.conv", zq, x0, B, h, w, e, 256, 3, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
+    tap("after_quant", x0, (size_t)B * h * w * 256);
+    float* d0 = up_block("decoder_group.0.block.1", "decoder_group.0.block.2", "decoder_group.0.block.3", x0, B, h, w, 256, 256, u1);
+    ar.release(x0);
+    tap("dec0", d0, (size_t)B * 2 * h * 2 * w * 256);
+    float* d1 = up_block("decoder_group.1.block.1", "decoder_group.1.block.2", "decoder_group.1.block.3", d0, B, 2 * h, 2 * w, 256, 128, u2);
+    ar.release(d0);
+    tap("dec1", d1, (size_t)B * 4 * h * 4 * w * 128);
+    float* d2 = up_block("decoder_group.2.block.1", "decoder_group.2.block.2", "decoder_group.2.block.3", d1, B, 4 * h, 4 * w, 128, 64, nullptr);
+    ar.release(d1);
+    tap("dec2", d2, (size_t)B * 8 * h * 8 * w * 64);
+    if (!dry() && ok())
+      check(femasr_out_conv3x3(d2, P("out_conv.weight"), P("out_conv.bias"), y_nchw, B, 8 * h, 8 * w, 64, st));
+    ar.release(d2);
+  }
+
+  void forward(const float* x_nchw, float* y_nchw, int64_t* indices, float* cb_loss, int B, int H, int W) {
+    const femasr_net_config& cfg = net->cfg;
+    const int d = net->depth, e = cfg.e_dim;
+    const std::string enc = "multiscale_encoder";
+    int c = chan(256 / cfg.scale_factor);
+    int h = H - 1, w = W - 1;
+    float* cur = ar.alloc((size_t)B * h * w * c);
+    if (!dry() && ok())
+      check(femasr_in_conv4x4(x_nchw, P(enc + ".in_conv.weight"), P(enc + ".in_conv.bias"), cur, B, cfg.in_channel, H, W, c, st));
+    tap("in_conv", cur, (size_t)B * h * w * c);
+    for (int i = 0; i < d; ++i) {
+      const std::string b = enc + ".blocks." + std::to_string(i);
+      const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1, co = 256;
+      float* nxt = ar.alloc((size_t)B * ho * wo * co);
+      conv(b + ".0", cur, nxt, B, h, w, c, co, 3, 2, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
+      ar.release(cur);
+      cur = nxt; h = ho; w = wo; c = co;
+      resblock(b + ".1", cur, B, h, w, c, nullptr);
+      resblock(b + ".2", cur, B, h, w, c, nullptr);
+    }
+    tap("down", cur, (size_t)B * h * w * c);
+    swin(enc + ".blocks." + std::to_string(d), cur, B, h, w);
+    tap("swin", cur, (size_t)B * h * w * c);
+    float *u1 = nullptr, *u2 = nullptr;
+    if (cfg.use_residual) {
+      const std::string b1 = enc + ".blocks." + std::to_string(d + 1), b2 = enc + ".blocks." + std::to_string(d + 2);
+      u1 = up_block(b1 + ".1", b1 + ".2", b1 + ".3", cur, B, h, w, 256, 256, nullptr);
+      tap("up1", u1, (size_t)B * 2 * h * 2 * w * 256);
+      u2 = up_block(b2 + ".1", b2 + ".2", b2 + ".3", u1, B, 2 * h, 2 * w, 256, 128, nullptr);
+      tap("up2", u2, (size_t)B * 4 * h * 4 * w * 128);
+    }
+    // feature matching
+    const size_t N = (size_t)B * h * w;
+    float* z = ar.alloc(N * e);
+    conv("before_quant_group.0", cur, z, B, h, w, 256, e, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
+    ar.release(cur);
+    tap("z", z, N * e);
+    float* zc = ar.alloc(N * cfg.n_e);
+    conv("quantize_group.0.embedding", z, zc, B, h, w, e, cfg.n_e, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, false);
+    float* zq = ar.alloc(N * e);
+    float* lrows = ar.alloc(N);
+    if (!dry() && ok()) {
+      check(femasr_vq_select(z, zc, net->raw["quantize_group.0.embedding.weight"].p, net->esq.p, indices, zq, lrows,
+                             (int)N, cfg.n_e, e, 0, st));
+      if (cb_loss && ok()) check(femasr_sum_scaled(lrows, cb_loss, N, 1.25 / ((double)N * e), st));
+    }
+    ar.release(lrows);
+    ar.release(zc);
+    tap("zq", zq, N * e);
+    decode(cfg.use_quantize ? zq : z, y_nchw, B, h, w, u1, u2);
+    if (u2) ar.release(u2);
+    if (u1) ar.release(u1);
+    ar.release(zq);
+    ar.release(z);
+  }
+
+  void decode_indices(const int64_t* idx, float* y_nchw, int B, int h, int w) {
+    const int e = net->cfg.e_dim;
+    const size_t N = (size_t)B * h * w;
+    float* zq = ar.alloc(N * e);
+    if (!dry() && ok())
+      check(femasr_codebook_gather(idx, net->raw["quantize_group.0.embedding.weight"].p, zq, (int)N, net->cfg.n_e, e, st));
+    decode(zq, y_nchw, B, h, w, nullptr, nullptr);
+    ar.release(zq);
+  }
+};
+
+static int check_geometry(femasr_net* net, int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return fail(FEMASR_ERR_ARG, "forward: empty input");
+  const int div = net->cfg.scale_factor == 4 ? 2 : 4;
+  if (H % 2 || W % 2) return fail(FEMASR_ERR_ARG, "forward: H and W must be even");
+  const int hs = H / div, ws = W / div;
+  if (H % div || W % div || hs % 8 || ws % 8 || hs == 0 || ws == 0)
+    return fail(FEMASR_ERR_ARG, "forward: Swin stage (H/" + std::to_string(div) + " x W/" + std::to_string(div) +
+                                    ") must be a non-empty multiple of the 8x8 window");
+  return FEMASR_OK;
+}
+
+}  // namespace femasr
+
+extern "C" const char* femasr_last_error(void) { return g_err.c_str(); }
+extern "C" int femasr_abi_version(void) { return 1; }
+
+extern "C" int femasr_device_cc(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(FEMASR_ERR_NO_DEVICE, "no CUDA device");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail(FEMASR_ERR_NO_DEVICE, "no CUDA device");
+  return prop.major * 10 + prop.minor;
+}
+
+extern "C" int femasr_net_create(const femasr_net_config* cfg, femasr_net** out) {
+  FEMASR_CHECK_ARG(cfg && out, "net_create: null pointer");
+  FEMASR_CHECK_ARG(cfg->scale_factor == 2 || cfg->scale_factor == 4, "net_create: scale_factor must be 2 or 4");
+  FEMASR_CHECK_ARG(cfg->in_channel == 3, "net_create: in_channel must be 3");
+  FEMASR_CHECK_ARG(cfg->e_dim > 0 && cfg->e_dim % 64 == 0 && cfg->e_dim <= 1024, "net_create: e_dim must be a multiple of 64");
+  FEMASR_CHECK_ARG(cfg->n_e > 0 && cfg->n_e % 64 == 0, "net_create: n_e must be a multiple of 64");
+  FEMASR_CHECK_ARG(cfg->gemm_path == 0 || cfg->gemm_path == 1, "net_create: gemm_path must be 0 or 1");
+  femasr_net* n = new femasr_net();
+  n->cfg = *cfg;
+  n->depth = cfg->scale_factor == 4 ? 1 : 2;
+  build_spec(n);
+  *out = n;
+  return FEMASR_OK;
+}
+
+extern "C" void femasr_net_destroy(femasr_net* net) { delete net; }
+
+extern "C" int femasr_net_set_param(femasr_net* net, const char* name, const float* data, size_t numel, int on_device,
+                                    void* stream) {
+  FEMASR_CHECK_ARG(net && name && data, "set_param: null pointer");
+  auto it = net->spec.find(name);
+  if (it == net->spec.end()) return fail(FEMASR_ERR_ARG, std::string("set_param: unknown parameter ") + name);
+  const ParamInfo& pi = it->second;
+  if (pi.numel != numel) return fail(FEMASR_ERR_ARG, std::string("set_param: wrong size for ") + name);
+  cudaStream_t st = as_stream(stream);
+  DevBuf& rb = net->raw[name];
+  if (!rb.p) { FEMASR_CUDA(cudaMalloc(&rb.p, numel * sizeof(float))); rb.n = numel; }
+  FEMASR_CUDA(cudaMemcpyAsync(rb.p, data, numel * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  if (!on_device) FEMASR_CUDA(cudaStreamSynchronize(st));   // the host buffer may be pageable / freed by the caller
+  std::string key(name);
+  if (pi.kind == 1) {
+    DevBuf& pb = net->packed[key];
+    if (!pb.p) { FEMASR_CUDA(cudaMalloc(&pb.p, numel * sizeof(float))); pb.n = numel; }
+    return femasr_pack_weight(rb.p, pb.p, pi.Cout, pi.Cin, pi.k, pi.k, st);
+  }
+  if (pi.kind == 2) {
+    DevBuf& pb = net->packed[key];
+    if (!pb.p) { FEMASR_CUDA(cudaMalloc(&pb.p, 8 * 64 * 64 * sizeof(float))); pb.n = 8 * 64 * 64; }
+    return femasr_expand_rel_bias(rb.p, pb.p, 8, st);
+  }
+  if (pi.kind == 3) {
+    DevBuf& pb = net->packed[key];     // codebook^T as a GEMM operand [e_dim][n_e]
+    if (!pb.p) { FEMASR_CUDA(cudaMalloc(&pb.p, numel * sizeof(float))); pb.n = numel; }
+    int s = femasr_pack_weight(rb.p, pb.p, pi.Cout, pi.Cin, 1, 1, st);
+    if (s) return s;
+    if (!net->esq.p) { FEMASR_CUDA(cudaMalloc(&net->esq.p, pi.Cout * sizeof(float))); net->esq.n = pi.Cout; }
+    return femasr_row_sumsq(rb.p, net->esq.p, pi.Cout, pi.Cin, st);
+  }
+  return FEMASR_OK;
+}
+
+extern "C" int femasr_net_params_complete(femasr_net* net) {
+  FEMASR_CHECK_ARG(net, "params_complete: null");
+  for (auto& kv : net->spec)
+    if (net->raw.find(kv.first) == net->raw.end()) return fail(FEMASR_ERR_STATE, "parameter not set: " + kv.first);
+  return FEMASR_OK;
+}
+
+extern "C" int femasr_net_workspace_bytes(femasr_net* net, int B, int H, int W, size_t* bytes) {
+  FEMASR_CHECK_ARG(net && bytes, "workspace_bytes: null pointer");
+  int s = check_geometry(net, B, H, W);
+  if (s) return s;
+  Ctx c; c.net = net; c.st = nullptr; c.ar.dry = true; c.ar.base = reinterpret_cast<char*>(uintptr_t(1) << 40);
+  c.forward(nullptr, nullptr, nullptr, nullptr, B, H, W);
+  *bytes = c.ar.peak + 256;
+  return c.status;
+}
+
+extern "C" int femasr_net_forward(femasr_net* net, const float* x, float* y, int64_t* indices, float* cb_loss, int B,
+                                  int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
+  FEMASR_CHECK_ARG(net && x && y && workspace, "forward: null pointer");
+  int s = check_geometry(net, B, H, W);
+  if (s) return s;
+  s = femasr_net_params_complete(net);
+  if (s) return s;
+  size_t need = 0;
+  s = femasr_net_workspace_bytes(net, B, H, W, &need);
+  if (s) return s;
+  const uintptr_t mis = (256 - ((uintptr_t)workspace & 255)) & 255;
+  if (workspace_bytes < need) return fail(FEMASR_ERR_STATE, "forward: workspace too small (need " + std::to_string(need) + " bytes)");
+  Ctx c; c.net = net; c.st = as_stream(stream); c.ar.dry = false;
+  c.ar.base = reinterpret_cast<char*>(workspace) + mis; c.ar.cap = workspace_bytes - mis;
+  const long l0 = g_launches;
+  c.forward(x, y, indices, cb_loss, B, H, W);
+  net->last_launches = (int)(g_launches - l0);
+  return c.status;
+}
+
+extern "C" int femasr_net_decode_workspace_bytes(femasr_net* net, int B, int h, int w, size_t* bytes) {
+  FEMASR_CHECK_ARG(net && bytes && B > 0 && h > 0 && w > 0, "decode_workspace_bytes: bad argument");
+  Ctx c; c.net = net; c.st = nullptr; c.ar.dry = true; c.ar.base = reinterpret_cast<char*>(uintptr_t(1) << 40);
+  c.decode_indices(nullptr, nullptr, B, h, w);
+  *bytes = c.ar.peak + 256;
+  return c.status;
+}
+
+extern "C" int femasr_net_decode_indices(femasr_net* net, const int64_t* indices, float* y, int B, int h, int w,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+  FEMASR_CHECK_ARG(net && indices && y && workspace && B > 0 && h > 0 && w > 0, "decode_indices: bad argument");
+  int s = femasr_net_params_complete(net);
+  if (s) return s;
+  size_t need = 0;
+  s = femasr_net_decode_workspace_bytes(net, B, h, w, &need);
+  if (s) return s;
+  if (workspace_bytes < need) return fail(FEMASR_ERR_STATE, "decode_indices: workspace too small");
+  const uintptr_t mis = (256 - ((uintptr_t)workspace & 255)) & 255;
+  Ctx c; c.net = net; c.st = as_stream(stream); c.ar.dry = false;
+  c.ar.base = reinterpret_cast<char*>(workspace) + mis;
+  const long l0 = g_launches;
+  c.decode_indices(indices, y, B, h, w);
+  net->last_launches = (int)(g_launches - l0);
+  return c.status;
+}
+
+extern "C" int femasr_net_set_tap(femasr_net* net, const char* stage, float* dst, size_t capacity) {
+  FEMASR_CHECK_ARG(net && stage, "set_tap: null pointer");
+  static const char* names[] = {"in_conv", "down", "swin", "up1", "up2", "z", "zq", "after_quant", "dec0", "dec1", "dec2"};
+  bool known = false;
+  for (const char* n : names) known = known || strcmp(n, stage) == 0;
+  if (!known) return fail(FEMASR_ERR_ARG, std::string("set_tap: unknown stage ") + stage);
+  if (dst) net->taps[stage] = Tap{dst, capacity};
+  else net->taps.erase(stage);
+  return FEMASR_OK;
+}
+
+extern "C" int femasr_net_last_launch_count(femasr_net* net) { return net ? net->last_launches : 0; }
+
+extern "C" double femasr_net_flops(femasr_net* net, int B, int H, int W) {
+  if (!net) return 0.0;
+  const int scale = net->cfg.scale_factor, d = net->depth, e = net->cfg.e_dim;
+  const double cin = chan(256 / scale);
+  double f = 2.0 * 3 * 16 * cin * (H - 1) * (double)(W - 1);
+  double ch = cin, hh = H, ww = W;
+  for (int i = 0; i < d; ++i) {
+    hh = std::floor(hh / 2); ww = std::floor(ww / 2);
+    f += 2.0 * 9 * ch * 256 * hh * ww + 4 * 2.0 * 9 * 256 * 256 * hh * ww;
+    ch = 256;
+  }
+  const double px = hh * ww;
+  const double lin = 2.0 * 256 * (768 + 256 + 1024 + 1024) * px, att = 2 * 2.0 * 64 * 256 * px;
+  f += 4 * (6 * (lin + att) + 2.0 * 9 * 256 * 256 * px);
+  f += 2.0 * 256 * e * px + 2.0 * net->cfg.n_e * e * px + 2.0 * 9 * e * 256 * px;
+  const double up[2][3] = {{256, 256, 2}, {256, 128, 4}};
+  for (auto& u : up) f += (2.0 * 9 * u[0] * u[1] + 4 * 2.0 * 9 * u[1] * u[1]) * px * u[2] * u[2];
+  const double dec[3][3] = {{256, 256, 2}, {256, 128, 4}, {128, 64, 8}};
+  for (auto& u : dec) f += (2.0 * 9 * u[0] * u[1] + 4 * 2.0 * 9 * u[1] * u[1]) * px * u[2] * u[2];
+  f += 2.0 * 9 * 64 * 3 * px * 64;
+  return f * B;
+}

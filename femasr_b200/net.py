@@ -1,0 +1,238 @@
+"""Host side of the B200-native FeMaSR path: owns the C engine handle, the device workspace and the
+test()/test_tile() scheduling.  PyTorch is used for device memory and the current stream only; all
+arithmetic happens in libfemasr_b200.so through the C ABI (include/femasr_b200.h).
+
+Mirrors the reference operator surface for this path (femasr_arch.py:311-479):
+encode_and_decode/forward -> NativeNet.forward, test -> NativeNet.test, test_tile -> NativeNet.test_tile,
+decode_indices -> NativeNet.decode_indices.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import lib as L
+from .spec import param_spec
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def tile_plan(height: int, width: int, tile_size: int, tile_pad: int) -> List[dict]:
+    """Tile windows of test_tile (femasr_arch.py:401-441): input window with halo clamped to the image,
+    output window, and the crop (offset inside the tile output, size), all in LR pixels."""
+    plan = []
+    for ty in range(math.ceil(height / tile_size)):
+        for tx in range(math.ceil(width / tile_size)):
+            x0, y0 = tx * tile_size, ty * tile_size
+            x1, y1 = min(x0 + tile_size, width), min(y0 + tile_size, height)
+            px0, px1 = max(x0 - tile_pad, 0), min(x1 + tile_pad, width)
+            py0, py1 = max(y0 - tile_pad, 0), min(y1 + tile_pad, height)
+            plan.append({"in": (py0, py1, px0, px1), "out": (y0, y1, x0, x1), "crop": (y0 - py0, x0 - px0)})
+    return plan
+
+
+def padded_size(n: int, scale: int) -> int:
+    """test() always pads to the NEXT multiple of wsz = 8//scale*8, even when n is one (femasr_arch.py:455-458)."""
+    wsz = 8 // scale * 8
+    return (n // wsz + 1) * wsz
+
+
+class NativeNet:
+    def __init__(self, scale_factor: int, n_e: int, e_dim: int, use_quantize: bool = True,
+                 use_residual: bool = True, gemm_path: int = 0):
+        self.lib = L.load()
+        self.scale = int(scale_factor)
+        self.n_e, self.e_dim = int(n_e), int(e_dim)
+        self.cfg = L.NetConfig(self.scale, self.n_e, self.e_dim, 3, int(bool(use_quantize)),
+                               int(bool(use_residual)), int(gemm_path))
+        self._h = C.c_void_p()
+        self._ws: Optional[torch.Tensor] = None
+        self._taps: Dict[str, torch.Tensor] = {}
+        self.device: Optional[torch.device] = None
+        self.names = [n for (n, _s, kind, _f) in param_spec(self.scale, self.e_dim, self.n_e)
+                      if kind not in ("rpi", "mask")]
+
+    # ------------------------------------------------------------------ lifecycle
+    def _ensure(self, device: torch.device):
+        if device.type != "cuda":
+            raise L.FemasrError("femasr_b200 runs on a CUDA sm_100 device only (no CPU fallback); "
+                                f"got tensors on '{device}'")
+        if self._h.value is None:
+            with torch.cuda.device(device):
+                L.require_device()
+                L.check(self.lib.femasr_net_create(C.byref(self.cfg), C.byref(self._h)))
+            self.device = device
+        elif device != self.device:
+            raise L.FemasrError(f"engine lives on {self.device}, input is on {device}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value is not None:
+            self.lib.femasr_net_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], device: torch.device):
+        """Upload every float parameter by its reference name (engine keeps repacked device copies)."""
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self._ensure(device)
+        with torch.cuda.device(device):
+            for name in self.names:
+                if name not in sd:
+                    raise L.FemasrError(f"state_dict is missing '{name}'")
+                t = sd[name].detach()
+                if t.dtype != torch.float32:
+                    t = t.float()
+                t = t.contiguous()
+                on_dev = t.device.type == "cuda"
+                if on_dev and t.device != device:
+                    t = t.to(device)
+                L.check(self.lib.femasr_net_set_param(self._h, name.encode(), t.data_ptr(), t.numel(),
+                                                      int(on_dev), _stream()))
+            L.check(self.lib.femasr_net_params_complete(self._h))
+            torch.cuda.current_stream().synchronize()
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ------------------------------------------------------------------ graph entry points
+    def forward(self, x: torch.Tensor, want_indices: bool = True, want_loss: bool = True,
+                taps: Optional[List[str]] = None):
+        """encode_and_decode.  x [B,3,H,W] fp32 cuda -> (y [B,3,sH,sW], loss scalar tensor | None,
+        indices [B,1,h,w] int64 | None[, {stage: NHWC tensor}])."""
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise L.FemasrError(f"expected input [B,3,H,W], got {tuple(x.shape)}")
+        self._ensure(x.device)
+        x = x.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        B, _, H, W = x.shape
+        s = self.scale
+        with torch.cuda.device(self.device):
+            need = C.c_size_t()
+            L.check(self.lib.femasr_net_workspace_bytes(self._h, B, H, W, C.byref(need)))
+            ws = self._workspace(need.value)
+            y = torch.empty((B, 3, H * s, W * s), dtype=torch.float32, device=self.device)
+            div = 2 if s == 4 else 4
+            h, w = H // div, W // div
+            idx = torch.empty((B, 1, h, w), dtype=torch.int64, device=self.device) if want_indices else None
+            loss = torch.empty((), dtype=torch.float32, device=self.device) if want_loss else None
+            tap_out = {}
+            if taps:
+                shapes = self.tap_shapes(B, H, W)
+                for name in taps:
+                    t = torch.empty(shapes[name], dtype=torch.float32, device=self.device)
+                    tap_out[name] = t
+                    L.check(self.lib.femasr_net_set_tap(self._h, name.encode(), t.data_ptr(), t.numel()))
+            try:
+                L.check(self.lib.femasr_net_forward(self._h, x.data_ptr(), y.data_ptr(), _ptr(idx), _ptr(loss),
+                                                    B, H, W, ws.data_ptr(), ws.numel(), _stream()))
+            finally:
+                for name in tap_out:
+                    self.lib.femasr_net_set_tap(self._h, name.encode(), None, 0)
+        if taps:
+            return y, loss, idx, tap_out
+        return y, loss, idx
+
+    def tap_shapes(self, B: int, H: int, W: int) -> Dict[str, Tuple[int, ...]]:
+        s = self.scale
+        div = 2 if s == 4 else 4
+        h, w = H // div, W // div
+        c0 = 256 if s == 4 else 128
+        return {"in_conv": (B, H - 1, W - 1, c0), "down": (B, h, w, 256), "swin": (B, h, w, 256),
+                "up1": (B, 2 * h, 2 * w, 256), "up2": (B, 4 * h, 4 * w, 128), "z": (B, h, w, self.e_dim),
+                "zq": (B, h, w, self.e_dim), "after_quant": (B, h, w, 256), "dec0": (B, 2 * h, 2 * w, 256),
+                "dec1": (B, 4 * h, 4 * w, 128), "dec2": (B, 8 * h, 8 * w, 64)}
+
+    def decode_indices(self, indices: torch.Tensor) -> torch.Tensor:
+        assert indices.dim() == 4, f"shape of indices must be (b, 1, h, w), but got {indices.shape}"
+        self._ensure(indices.device)
+        idx = indices.detach().to(torch.int64).contiguous()
+        B, _, h, w = idx.shape
+        with torch.cuda.device(self.device):
+            need = C.c_size_t()
+            L.check(self.lib.femasr_net_decode_workspace_bytes(self._h, B, h, w, C.byref(need)))
+            ws = self._workspace(need.value)
+            y = torch.empty((B, 3, 8 * h, 8 * w), dtype=torch.float32, device=self.device)
+            L.check(self.lib.femasr_net_decode_indices(self._h, idx.data_ptr(), y.data_ptr(), B, h, w,
+                                                       ws.data_ptr(), ws.numel(), _stream()))
+        return y
+
+    def last_launch_count(self) -> int:
+        return int(self.lib.femasr_net_last_launch_count(self._h))
+
+    def flops(self, B: int, H: int, W: int) -> float:
+        return float(self.lib.femasr_net_flops(self._h, B, H, W))
+
+    # ------------------------------------------------------------------ test() / test_tile()
+    def test(self, x: torch.Tensor) -> torch.Tensor:
+        """femasr_arch.py:449-468: flip-pad, encode_and_decode, crop."""
+        self._ensure(x.device)
+        x = x.detach().float().contiguous()
+        B, Cc, h, w = x.shape
+        s = self.scale
+        hp, wp = padded_size(h, s), padded_size(w, s)
+        with torch.cuda.device(self.device):
+            xp = torch.empty((B, Cc, hp, wp), dtype=torch.float32, device=self.device)
+            L.check(self.lib.femasr_flip_pad(x.data_ptr(), xp.data_ptr(), B, Cc, h, w, hp, wp, _stream()))
+            yp, _, _ = self.forward(xp, want_indices=False, want_loss=False)
+            y = torch.empty((B, 3, h * s, w * s), dtype=torch.float32, device=self.device)
+            L.check(self.lib.femasr_copy_window(yp.data_ptr(), y.data_ptr(), B, 3, hp * s, wp * s, h * s, w * s,
+                                                0, 0, 0, 0, h * s, w * s, _stream()))
+        return y
+
+    def test_tile(self, x: torch.Tensor, tile_size: int = 240, tile_pad: int = 16,
+                  max_batch: int = 64) -> torch.Tensor:
+        """femasr_arch.py:387-447.  Tiles are independent (every op on the path is per-sample), so
+        same-shape tiles are stacked into one batch per forward instead of the reference's
+        one-tile-at-a-time loop; results are identical per tile."""
+        self._ensure(x.device)
+        x = x.detach().float().contiguous()
+        B, Cc, H, W = x.shape
+        s = self.scale
+        plan = tile_plan(H, W, tile_size, tile_pad)
+        groups: Dict[Tuple[int, int], List[dict]] = {}
+        for t in plan:
+            py0, py1, px0, px1 = t["in"]
+            groups.setdefault((py1 - py0, px1 - px0), []).append(t)
+        with torch.cuda.device(self.device):
+            out = torch.zeros((B, Cc, H * s, W * s), dtype=torch.float32, device=self.device)
+            st = _stream()
+            for (th, tw), tiles in groups.items():
+                per = max(1, max_batch // B)
+                for i in range(0, len(tiles), per):
+                    chunk = tiles[i:i + per]
+                    tb = torch.empty((len(chunk) * B, Cc, th, tw), dtype=torch.float32, device=self.device)
+                    for k, t in enumerate(chunk):
+                        py0, _py1, px0, _px1 = t["in"]
+                        dst = tb.data_ptr() + k * B * Cc * th * tw * 4
+                        L.check(self.lib.femasr_copy_window(x.data_ptr(), dst, B, Cc, H, W, th, tw,
+                                                            py0, px0, 0, 0, th, tw, st))
+                    yt = self.test(tb)
+                    for k, t in enumerate(chunk):
+                        y0, y1, x0, x1 = t["out"]
+                        cy, cx = t["crop"]
+                        src = yt.data_ptr() + k * B * Cc * th * s * tw * s * 4
+                        L.check(self.lib.femasr_copy_window(src, out.data_ptr(), B, Cc, th * s, tw * s, H * s, W * s,
+                                                            cy * s, cx * s, y0 * s, x0 * s, (y1 - y0) * s,
+                                                            (x1 - x0) * s, st))
+        return out

@@ -1,0 +1,182 @@
+/* femasr_b200.h - C ABI of the B200-native FeMaSR inference hot path.
+ *
+ * This shared library (libfemasr_b200.so, sm_100a only) is the drop-in boundary underneath the
+ * reference's Python operator surface `basicsr.archs.femasr_arch.FeMaSRNet`
+ * (/root/reference/basicsr/archs/femasr_arch.py:214-479).  Signatures use plain pointers and
+ * sizes only: device pointers are raw CUDA addresses, `stream` is a cudaStream_t passed as void*.
+ * Every entry point returns 0 on success or a negative femasr_status; femasr_last_error() gives
+ * the message (thread-local).  Nothing here owns caller memory; nothing falls back to the CPU.
+ *
+ * Data layout: activations between kernels are NHWC fp32 ([B,H,W,C]; Swin tokens [B,HW,C] are the
+ * same bytes).  Images at the public boundary are NCHW fp32 like the reference's tensors.
+ */
+#ifndef FEMASR_B200_H
+#define FEMASR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  FEMASR_OK = 0,
+  FEMASR_ERR_ARG = -1,       /* bad shape / null pointer / unsupported configuration */
+  FEMASR_ERR_CUDA = -2,      /* a CUDA runtime/driver call failed */
+  FEMASR_ERR_STATE = -3,     /* missing parameter, workspace too small, ... */
+  FEMASR_ERR_NO_DEVICE = -4  /* no sm_100 device: there is no CPU fallback */
+} femasr_status;
+
+const char* femasr_last_error(void);
+int femasr_abi_version(void);
+/* compute capability major*10+minor of the current device, or negative status */
+int femasr_device_cc(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Network-level API: replaces FeMaSRNet.encode_and_decode / test / decode_indices
+ * (femasr_arch.py:311-374, 449-468, 376-385) for LQ_stage=True, norm 'gn', act 'silu',
+ * one codebook at scale 32, scale_factor 2 or 4.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct femasr_net femasr_net;
+
+typedef struct {
+  int scale_factor;   /* 2 or 4            (femasr_arch.py:225) */
+  int n_e;            /* codebook entries  (codebook_params[0][1]) */
+  int e_dim;          /* codebook dim      (codebook_params[0][2]), multiple of 64 */
+  int in_channel;     /* 3 */
+  int use_quantize;   /* femasr_arch.py:224,349-350: 0 => z_quant = feat_to_quant (VQ still runs) */
+  int use_residual;   /* femasr_arch.py:226,361-362 */
+  int gemm_path;      /* 0 = fp32 SIMT implicit GEMM, 1 = tcgen05 split-fp16 tensor-core GEMM */
+} femasr_net_config;
+
+int femasr_net_create(const femasr_net_config* cfg, femasr_net** out);
+void femasr_net_destroy(femasr_net* net);
+
+/* Upload one state_dict tensor by its reference name, fp32, contiguous, from HOST
+ * or DEVICE memory (`on_device` says which).  The engine keeps its own repacked device copy.
+ * int64 buffers (relative_position_index, attn_mask) are derived, not uploaded. */
+int femasr_net_set_param(femasr_net* net, const char* name, const float* data, size_t numel,
+                         int on_device, void* stream);
+/* 0 if every parameter has been set, else FEMASR_ERR_STATE (message names the first missing). */
+int femasr_net_params_complete(femasr_net* net);
+
+/* Bytes of device workspace femasr_net_forward needs for a [B,3,H,W] input. */
+int femasr_net_workspace_bytes(femasr_net* net, int B, int H, int W, size_t* bytes);
+
+/* encode_and_decode (femasr_arch.py:311-374).
+ *   x_nchw    [B,3,H,W] fp32 device.  H,W such that the Swin stage (H/2 for x4, H/4 for x2) is a
+ *             multiple of 8, else FEMASR_ERR_ARG (the reference raises from window_partition).
+ *   y_nchw    [B,3,s*H,s*W] fp32 device, unclamped.
+ *   indices   [B,1,h,w] int64 device (may be NULL).
+ *   cb_loss   1 float device: codebook_loss = 1.25*mean((z_q-z)^2) (femasr_arch.py:84-92); may be NULL.
+ */
+int femasr_net_forward(femasr_net* net, const float* x_nchw, float* y_nchw, int64_t* indices,
+                       float* cb_loss, int B, int H, int W, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* decode_indices (femasr_arch.py:376-385): indices [B,1,h,w] int64 -> y [B,3,8h,8w]. */
+int femasr_net_decode_indices(femasr_net* net, const int64_t* indices, float* y_nchw, int B, int h,
+                              int w, void* workspace, size_t workspace_bytes, void* stream);
+int femasr_net_decode_workspace_bytes(femasr_net* net, int B, int h, int w, size_t* bytes);
+
+/* Stage taps for parity tests: when `dst` is set for a stage name, the next forward copies that
+ * stage's NHWC fp32 tensor there (device, `capacity` floats).  Names: in_conv, down, swin, up1, up2,
+ * z, zq, after_quant, dec0, dec1, dec2.  dst == NULL removes the tap. */
+int femasr_net_set_tap(femasr_net* net, const char* stage, float* dst, size_t capacity);
+/* Number of kernels the last femasr_net_forward launched (bench.py's gpu_launches). */
+int femasr_net_last_launch_count(femasr_net* net);
+/* Algorithmic FLOPs (2*MAC, conv+linear+QK/PV+VQ distance) of one forward on [B,3,H,W]. */
+double femasr_net_flops(femasr_net* net, int B, int H, int W);
+
+/* test() padding (femasr_arch.py:455-460): flip-pad [B,3,h,w] -> [B,3,hp,wp]. */
+int femasr_flip_pad(const float* x, float* y, int B, int C, int h, int w, int hp, int wp, void* stream);
+/* crop / paste used by test() (:465) and test_tile() (:444-446): copies the window
+ * src[:, :, sy:sy+ch, sx:sx+cw] to dst[:, :, dy:dy+ch, dx:dx+cw]. */
+int femasr_copy_window(const float* src, float* dst, int B, int C, int sh, int sw, int dh, int dw,
+                       int sy, int sx, int dy, int dx, int ch, int cw, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Operator-level API (what the network is built from; exported so each kernel has its own parity
+ * test).  All tensors device fp32 unless stated.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Repack a conv weight OIHW [Cout,Cin,kh,kw] -> K-major GEMM operand [kh*kw*Cin][Cout]
+ * (linear weights [N,K] are the kh=kw=1 case). */
+int femasr_pack_weight(const float* w_oihw, float* w_packed, int Cout, int Cin, int kh, int kw, void* stream);
+
+enum { FEMASR_PRO_NONE = 0, FEMASR_PRO_GN_SILU = 1, FEMASR_PRO_LN = 2 };
+enum { FEMASR_ACT_NONE = 0, FEMASR_ACT_GELU = 1 };
+
+/* Implicit-GEMM convolution / linear:  y = act(conv(pro(x)) + bias) + res1 + res2.
+ *   ksize 3 (pad 1) or 1 (pad 0); stride 1|2; upsample=1 applies nearest x2 to pro(x) first
+ *   (nn.Upsample, femasr_arch.py:172,202).  Linear layers are ksize=1 with Hin*Win = tokens.
+ *   prologue GN_SILU: x' = silu(x*pro_scale[b,c] + pro_shift[b,c])   (tables from femasr_gn_stats)
+ *   prologue LN:      x' = (x - row_mean[m])*row_rstd[m]*gamma[c] + beta[c]
+ * Replaces nn.Conv2d / nn.Linear call sites femasr_arch.py:150-203,273,298; fema_utils.py:75-90;
+ * network_swinir.py:19-21,105-107,465. */
+typedef struct {
+  const float* x;          /* NHWC [B,Hin,Win,Cin] */
+  const float* w;          /* packed [ksize*ksize*Cin][Cout] */
+  const float* bias;       /* [Cout] or NULL */
+  const float* res1;       /* NHWC like y, or NULL; may alias y */
+  const float* res2;       /* NHWC like y, or NULL */
+  float* y;                /* NHWC [B,Ho,Wo,Cout] */
+  const float* pro_a;      /* GN: scale [B,Cin];  LN: row_mean [M] */
+  const float* pro_b;      /* GN: shift [B,Cin];  LN: row_rstd [M] */
+  const float* gamma;      /* LN only: [Cin] */
+  const float* beta;       /* LN only: [Cin] */
+  int B, Hin, Win, Cin, Cout;
+  int ksize, stride, upsample;
+  int prologue;            /* FEMASR_PRO_* */
+  int act;                 /* FEMASR_ACT_* */
+} femasr_igemm_args;
+int femasr_igemm_simt(const femasr_igemm_args* a, void* stream);
+
+/* GroupNorm(32 groups, eps) statistics of NHWC x[B,HW,C] folded with the affine parameters into
+ * per-(sample,channel) scale/shift: scale = rstd*gamma, shift = beta - mean*rstd*gamma
+ * (nn.GroupNorm, fema_utils.py:21-22).  `scratch` >= femasr_gn_scratch_floats(B,HW,C) floats. */
+size_t femasr_gn_scratch_floats(int B, int HW, int C);
+int femasr_gn_stats(const float* x, const float* gamma, const float* beta, float* scale, float* shift,
+                    float* scratch, int B, int HW, int C, float eps, void* stream);
+
+/* LayerNorm statistics per token row of x[M,C] (C == 256): mean[M], rstd[M] (network_swinir.py:199,207). */
+int femasr_ln_stats(const float* x, float* mean, float* rstd, int M, int C, float eps, void* stream);
+
+/* Shifted-window multi-head attention (network_swinir.py:114-145, 239-279 minus the linears):
+ * qkv [B*H*W, 3*C] in token order -> out [B*H*W, C] in token order; 8x8 windows, C = heads*32,
+ * cyclic shift `shift` (0 or 4) and its 0/-100 mask are applied by index arithmetic.
+ * bias_full [heads][64][64] = relative_position_bias_table[relative_position_index] (:127-129). */
+int femasr_window_attention(const float* qkv, const float* bias_full, float* out, int B, int H, int W,
+                            int C, int heads, int shift, void* stream);
+int femasr_expand_rel_bias(const float* table /*[225,heads]*/, float* bias_full, int heads, void* stream);
+
+/* VectorQuantizer.forward (femasr_arch.py:50-100) given zc = z @ codebook^T:
+ *   d_j = fl(fl(sum z^2 + esq_j) - 2*zc_j), idx = argmin (lowest index on ties), zq = z + (e_idx - z),
+ *   loss_rows[i] = sum_k (e_idx - z)^2.  esq from femasr_row_sumsq(codebook). */
+int femasr_row_sumsq(const float* x, float* out, int rows, int cols, void* stream);
+int femasr_vq_select(const float* z, const float* zc, const float* codebook, const float* esq,
+                     int64_t* idx, float* zq, float* loss_rows, int N, int n_e, int e_dim,
+                     int write_zq_passthrough, void* stream);
+/* out[0] = scale * sum(x[0..n)) accumulated in double in a fixed order. */
+int femasr_sum_scaled(const float* x, float* out, size_t n, double scale, void* stream);
+/* get_codebook_entry (femasr_arch.py:102-112): zq[N,e] = codebook[idx]. */
+int femasr_codebook_gather(const int64_t* idx, const float* codebook, float* zq, int N, int n_e,
+                           int e_dim, void* stream);
+
+/* MultiScaleEncoder.in_conv (femasr_arch.py:150): 4x4, pad 1, NCHW [B,Cin,H,W] -> NHWC [B,H-1,W-1,Cout].
+ * w packed [16*Cin][Cout]. */
+int femasr_in_conv4x4(const float* x_nchw, const float* w, const float* bias, float* y_nhwc, int B,
+                      int Cin, int H, int W, int Cout, void* stream);
+/* out_conv (femasr_arch.py:273): 3x3 pad 1, NHWC [B,H,W,Cin] -> NCHW [B,3,H,W].  w packed [9*Cin][3]. */
+int femasr_out_conv3x3(const float* x_nhwc, const float* w, const float* bias, float* y_nchw, int B,
+                       int H, int W, int Cin, void* stream);
+
+/* layout helpers for tests */
+int femasr_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, void* stream);
+int femasr_nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMASR_B200_H */

@@ -1,0 +1,66 @@
+"""Thin torch-tensor wrappers over the C ABI for the GPU parity tests."""
+import ctypes as C
+
+import torch
+
+from femasr_b200 import lib as L
+
+
+def S():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def p(t):
+    return None if t is None else t.data_ptr()
+
+
+def nhwc(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x_nhwc):
+    return x_nhwc.permute(0, 3, 1, 2).contiguous()
+
+
+def pack_weight(w_oihw):
+    lib = L.load()
+    co, ci, kh, kw = w_oihw.shape
+    out = torch.empty(kh * kw * ci, co, device=w_oihw.device)
+    L.check(lib.femasr_pack_weight(p(w_oihw.contiguous()), p(out), co, ci, kh, kw, S()))
+    return out
+
+
+def igemm(x, w_packed, bias, B, Hin, Win, Cin, Cout, ksize=3, stride=1, upsample=0, prologue=0, pro_a=None,
+          pro_b=None, gamma=None, beta=None, act=0, res1=None, res2=None, fn="femasr_igemm_simt"):
+    lib = L.load()
+    He, We = (2 * Hin, 2 * Win) if upsample else (Hin, Win)
+    if ksize == 1:
+        Ho, Wo = Hin, Win
+    elif stride == 1:
+        Ho, Wo = He, We
+    else:
+        Ho, Wo = (He - 1) // 2 + 1, (We - 1) // 2 + 1
+    y = torch.empty(B, Ho, Wo, Cout, device=x.device)
+    a = L.IgemmArgs(p(x), p(w_packed), p(bias), p(res1), p(res2), p(y), p(pro_a), p(pro_b), p(gamma), p(beta),
+                    B, Hin, Win, Cin, Cout, ksize, stride, upsample, prologue, act)
+    L.check(getattr(lib, fn)(C.byref(a), S()))
+    return y
+
+
+def gn_tables(x_nhwc, gamma, beta, eps=1e-6):
+    lib = L.load()
+    B, H, W, Cc = x_nhwc.shape
+    sc = torch.empty(B, Cc, device=x_nhwc.device)
+    sh = torch.empty(B, Cc, device=x_nhwc.device)
+    scratch = torch.empty(max(1, lib.femasr_gn_scratch_floats(B, H * W, Cc)), device=x_nhwc.device)
+    L.check(lib.femasr_gn_stats(p(x_nhwc), p(gamma), p(beta), p(sc), p(sh), p(scratch), B, H * W, Cc, eps, S()))
+    return sc, sh
+
+
+def ln_stats(x_tokens, eps=1e-5):
+    lib = L.load()
+    M, Cc = x_tokens.shape
+    mu = torch.empty(M, device=x_tokens.device)
+    rs = torch.empty(M, device=x_tokens.device)
+    L.check(lib.femasr_ln_stats(p(x_tokens), p(mu), p(rs), M, Cc, eps, S()))
+    return mu, rs

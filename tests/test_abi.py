@@ -1,0 +1,67 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/femasr_b200.h declares;
+without a GPU the product path fails loudly instead of falling back."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "femasr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(femasr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from femasr_b200 import lib
+    names = header_symbols()
+    assert len(names) >= 30
+    dll = ctypes.CDLL(built_lib)
+    for n in names:
+        assert hasattr(dll, n), f"{n} declared in the header but not exported"
+    assert sorted(lib.SIGNATURES) == names, "femasr_b200/lib.py SIGNATURES out of sync with the header"
+    assert lib.load().femasr_abi_version() == 1
+
+
+def test_argument_validation_without_gpu(built_lib):
+    from femasr_b200 import lib
+    L = lib.load()
+    a = lib.IgemmArgs()
+    assert L.femasr_igemm_simt(ctypes.byref(a), None) == -1
+    assert b"null" in L.femasr_last_error()
+    h = ctypes.c_void_p()
+    cfg = lib.NetConfig(3, 1024, 256, 3, 1, 1, 0)
+    assert L.femasr_net_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    cfg = lib.NetConfig(4, 1024, 256, 3, 1, 1, 0)
+    assert L.femasr_net_create(ctypes.byref(cfg), ctypes.byref(h)) == 0
+    need = ctypes.c_size_t()
+    # 40x40: Swin stage 20x20 is not a multiple of the 8x8 window -> the reference raises in window_partition
+    assert L.femasr_net_workspace_bytes(h, 1, 40, 40, ctypes.byref(need)) == -1
+    assert L.femasr_net_workspace_bytes(h, 32, 128, 128, ctypes.byref(need)) == 0
+    assert 1 << 30 < need.value < 40 << 30
+    assert abs(L.femasr_net_flops(h, 1, 128, 128) / 1e9 - 754.53) < 0.01
+    assert L.femasr_net_params_complete(h) == -3
+    L.femasr_net_destroy(h)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(built_lib):
+    from basicsr.archs.femasr_arch import FeMaSRNet
+    from femasr_b200.lib import FemasrError
+    net = FeMaSRNet(codebook_params=[[32, 1024, 256]], LQ_stage=True, scale_factor=4).eval()
+    with pytest.raises(FemasrError):
+        net.test(torch.rand(1, 3, 32, 32))
+    with pytest.raises(FemasrError):
+        net(torch.rand(1, 3, 32, 32))
+
+
+def test_unsupported_configs_raise():
+    from basicsr.archs.femasr_arch import FeMaSRNet
+    with pytest.raises(NotImplementedError):
+        FeMaSRNet(codebook_params=[[32, 1024, 256]], LQ_stage=False)
+    with pytest.raises(NotImplementedError):
+        FeMaSRNet(codebook_params=[[32, 1024, 256], [64, 512, 256]], LQ_stage=True)

@@ -1,0 +1,223 @@
+"""GPU: every exported operator kernel against the same ATen op on CPU fp32 (the arithmetic the
+reference runs), through the C ABI.  Tolerances are fp32-summation-order bounds, written per test."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from femasr_b200 import lib as L
+from femasr_b200.spec import relative_position_index, shift_attn_mask
+from oracle import femasr_oracle as O
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def close(got, want, atol, what=""):
+    err = (got.cpu() - want).abs().max().item()
+    assert err <= atol, f"{what}: max-abs {err:.3e} > {atol:.1e}"
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride,up", [
+    (2, 16, 24, 64, 64, 1, 0), (1, 9, 11, 128, 256, 1, 0), (2, 15, 13, 256, 256, 2, 0),
+    (1, 8, 8, 256, 128, 1, 1), (1, 6, 10, 128, 64, 1, 1), (3, 8, 8, 512, 256, 1, 0)])
+def test_conv3x3(cuda, B, H, W, Cin, Cout, stride, up):
+    x, w, b = rnd(B, Cin, H, W, seed=1), rnd(Cout, Cin, 3, 3, seed=2, scale=0.05), rnd(Cout, seed=3)
+    xin = O.upsample2(x) if up else x
+    want = F.conv2d(xin, w, b, stride=stride, padding=1)
+    y = G.igemm(G.nhwc(x).to(cuda), G.pack_weight(w.to(cuda)), b.to(cuda), B, H, W, Cin, Cout, 3, stride, up)
+    close(G.nchw(y), want, 2e-5 * (Cin * 9) ** 0.5, "conv3x3")
+
+
+def test_conv3x3_gn_silu_residuals(cuda):
+    B, H, W, Cc = 2, 12, 20, 128
+    x, w, b = rnd(B, Cc, H, W, seed=4, scale=2.0) + 0.5, rnd(Cc, Cc, 3, 3, seed=5, scale=0.03), rnd(Cc, seed=6)
+    gamma, beta = 1 + 0.2 * rnd(Cc, seed=7), 0.2 * rnd(Cc, seed=8)
+    r1, r2 = rnd(B, Cc, H, W, seed=9), rnd(B, Cc, H, W, seed=10)
+    t = F.silu(F.group_norm(x, 32, gamma, beta, 1e-6))
+    want = (F.conv2d(t, w, b, padding=1) + r1) + r2
+    xg = G.nhwc(x).to(cuda)
+    sc, sh = G.gn_tables(xg, gamma.to(cuda), beta.to(cuda))
+    y = G.igemm(xg, G.pack_weight(w.to(cuda)), b.to(cuda), B, H, W, Cc, Cc, 3, 1, 0, L.PRO_GN_SILU, sc, sh,
+                res1=G.nhwc(r1).to(cuda), res2=G.nhwc(r2).to(cuda))
+    close(G.nchw(y), want, 1e-4, "gn+silu conv")
+
+
+@pytest.mark.parametrize("C_", [64, 128, 256])
+def test_gn_tables(cuda, C_):
+    B, H, W = 3, 37, 29    # HW = 1073: partial chunks
+    x = rnd(B, C_, H, W, seed=11, scale=3.0) + 1.5
+    gamma, beta = 1 + 0.2 * rnd(C_, seed=12), 0.2 * rnd(C_, seed=13)
+    want = F.group_norm(x, 32, gamma, beta, 1e-6)
+    sc, sh = G.gn_tables(G.nhwc(x).to(cuda), gamma.to(cuda), beta.to(cuda))
+    got = x * sc.cpu()[:, :, None, None] + sh.cpu()[:, :, None, None]
+    close(got, want, 5e-6, "group norm")
+
+
+def test_linear_ln_gelu_residual(cuda):
+    M, K, N = 333, 256, 1024
+    x, w, b = rnd(M, K, seed=14, scale=2.0) + 0.3, rnd(N, K, seed=15, scale=0.05), rnd(N, seed=16)
+    gamma, beta = 1 + 0.2 * rnd(K, seed=17), 0.2 * rnd(K, seed=18)
+    want = F.gelu(F.linear(F.layer_norm(x, (K,), gamma, beta, 1e-5), w, b))
+    xg = x.to(cuda)
+    mu, rs = G.ln_stats(xg)
+    y = G.igemm(xg, G.pack_weight(w.view(N, K, 1, 1).to(cuda)), b.to(cuda), 1, 1, M, K, N, 1, 1, 0, L.PRO_LN, mu, rs,
+                gamma.to(cuda), beta.to(cuda), act=L.ACT_GELU)
+    close(y.view(M, N), want, 5e-5, "ln+linear+gelu")
+    # fc2-like: K=1024 -> 256 with in-place residual
+    w2, b2 = rnd(K, N, seed=19, scale=0.03), rnd(K, seed=20)
+    res = rnd(M, K, seed=21).to(cuda)
+    want2 = F.linear(want, w2, b2) + res.cpu()
+    h = want.to(cuda).contiguous()
+    w2p, b2g = G.pack_weight(w2.view(K, N, 1, 1).to(cuda)), b2.to(cuda)
+    a = L.IgemmArgs(h.data_ptr(), w2p.data_ptr(), b2g.data_ptr(),
+                    res.data_ptr(), None, res.data_ptr(), None, None, None, None, 1, 1, M, N, K, 1, 1, 0, 0, 0)
+    L.check(L.load().femasr_igemm_simt(C.byref(a), G.S()))
+    close(res.view(M, K), want2, 1e-4, "linear + in-place residual")
+
+
+@pytest.mark.parametrize("H,W,shift", [(16, 24, 0), (16, 24, 4), (8, 8, 4), (72, 8, 4)])
+def test_window_attention(cuda, H, W, shift):
+    B, Cc = 2, 256
+    qkv = rnd(B, H * W, 3 * Cc, seed=22)
+    table = rnd(225, 8, seed=23, scale=0.5)
+    # reference semantics via the oracle helpers (network_swinir.py:114-145,239-279)
+    t = qkv.view(B, H, W, 3 * Cc)
+    if shift:
+        t = torch.roll(t, (-shift, -shift), (1, 2))
+    tw = O.window_partition(t, 8)
+    q, k, v = tw.reshape(-1, 64, 3, 8, 32).permute(2, 0, 3, 1, 4)
+    attn = (q * 32 ** -0.5) @ k.transpose(-2, -1)
+    bias = table[relative_position_index().view(-1)].view(64, 64, 8).permute(2, 0, 1)
+    attn = attn + bias.unsqueeze(0)
+    if shift:
+        mask = O.shift_mask(H, W, 8, shift, torch.float32)
+        assert torch.equal(mask, shift_attn_mask(H, W, 8, shift))
+        nW = mask.shape[0]
+        attn = (attn.view(-1, nW, 8, 64, 64) + mask[None, :, None]).view(-1, 8, 64, 64)
+    o = (attn.softmax(-1) @ v).transpose(1, 2).reshape(-1, 64, Cc)
+    o = O.window_reverse(o, 8, H, W)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    want = o.reshape(B, H * W, Cc)
+    lib = L.load()
+    tb = table.to(cuda)
+    full = torch.empty(8, 64, 64, device=cuda)
+    L.check(lib.femasr_expand_rel_bias(tb.data_ptr(), full.data_ptr(), 8, G.S()))
+    close(full, bias, 0.0, "rel-pos bias expansion")
+    out = torch.empty(B, H * W, Cc, device=cuda)
+    qkvg = qkv.to(cuda)
+    L.check(lib.femasr_window_attention(qkvg.data_ptr(), full.data_ptr(), out.data_ptr(), B, H, W, Cc, 8, shift, G.S()))
+    close(out, want, 2e-5, "window attention")
+
+
+@pytest.mark.parametrize("e_dim,init", [(256, "tiny"), (512, "tiny"), (256, "wide")])
+def test_vq_select_bit_exact(cuda, e_dim, init):
+    """Indices must be bit-exact given the same z and the same z.e^T (here: ATen's own matmul result, so
+    the test isolates the distance formula + tie rule; ties are frequent with the U(+-1/1024) codebook)."""
+    N, n_e = 4096, 1024
+    g = torch.Generator().manual_seed(24)
+    z = torch.randn(N, e_dim, generator=g) * 1.1
+    cb = (torch.rand(n_e, e_dim, generator=g) * 2 - 1) / n_e if init == "tiny" else torch.randn(n_e, e_dim, generator=g)
+    zc = z @ cb.t()
+    d = O.vq_dist(z, cb)
+    assert torch.equal(d, torch.sum(z ** 2, 1, keepdim=True) + torch.sum(cb ** 2, 1) - 2 * zc)
+    want_idx = torch.argmin(d, 1)
+    lib = L.load()
+    zg, cbg, zcg = z.to(cuda), cb.to(cuda), zc.to(cuda)
+    esq = torch.sum(cb ** 2, 1).to(cuda)     # ATen's B_j: isolates the select kernel
+    idx = torch.empty(N, dtype=torch.int64, device=cuda)
+    zq = torch.empty(N, e_dim, device=cuda)
+    lrows = torch.empty(N, device=cuda)
+    # A = sum z^2 is computed in-kernel with a different summation order than ATen; the argmin is invariant
+    # to 1-ulp shifts of A (all d_j move together), see DESIGN.md "VQ rounding".
+    L.check(lib.femasr_vq_select(zg.data_ptr(), zcg.data_ptr(), cbg.data_ptr(), esq.data_ptr(), idx.data_ptr(),
+                                 zq.data_ptr(), lrows.data_ptr(), N, n_e, e_dim, 0, G.S()))
+    mism = (idx.cpu() != want_idx).sum().item()
+    assert mism == 0, f"{mism}/{N} index mismatches"
+    e = cb[want_idx]
+    want_zq = z + (e - z)
+    assert torch.equal(zq.cpu(), want_zq), "straight-through z + (e - z) must be bit-exact"
+    loss = torch.empty((), device=cuda)
+    L.check(lib.femasr_sum_scaled(lrows.data_ptr(), loss.data_ptr(), N, 1.25 / (N * e_dim), G.S()))
+    want_loss = torch.mean((e - z) ** 2) * 1.25
+    assert abs(loss.item() - want_loss.item()) <= 2e-6 * abs(want_loss.item())
+    # own esq kernel: fp32-accurate
+    esq2 = torch.empty(n_e, device=cuda)
+    L.check(lib.femasr_row_sumsq(cbg.data_ptr(), esq2.data_ptr(), n_e, e_dim, G.S()))
+    assert (esq2.cpu() - esq.cpu()).abs().max().item() <= 4e-7 * esq.abs().max().item()
+
+
+def test_vq_ties_pick_lowest_index(cuda):
+    N, n_e, e_dim = 64, 1024, 256
+    z = rnd(N, e_dim, seed=25)
+    cb = rnd(n_e, e_dim, seed=26)
+    cb[700] = cb[3]
+    cb[512] = cb[3]          # exact duplicates of code 3
+    z[:] = cb[3] + 1e-3 * rnd(N, e_dim, seed=27)
+    zc = z @ cb.t()
+    lib = L.load()
+    idx = torch.empty(N, dtype=torch.int64, device=cuda)
+    esq = torch.sum(cb ** 2, 1).to(cuda)
+    zg, zcg, cbg = z.to(cuda), zc.to(cuda), cb.to(cuda)
+    L.check(lib.femasr_vq_select(zg.data_ptr(), zcg.data_ptr(), cbg.data_ptr(),
+                                 esq.data_ptr(), idx.data_ptr(), None, None, N, n_e, e_dim, 0, G.S()))
+    assert (idx.cpu() == 3).all()
+
+
+def test_in_conv_out_conv(cuda):
+    lib = L.load()
+    B, H, W = 2, 18, 22
+    for cout in (256, 128):
+        x, w, b = torch.rand(B, 3, H, W), rnd(cout, 3, 4, 4, seed=28, scale=0.15), rnd(cout, seed=29)
+        want = F.conv2d(x, w, b, padding=1)
+        y = torch.empty(B, H - 1, W - 1, cout, device=cuda)
+        xg, wp, bg = x.to(cuda), G.pack_weight(w.to(cuda)), b.to(cuda)
+        L.check(lib.femasr_in_conv4x4(xg.data_ptr(), wp.data_ptr(), bg.data_ptr(), y.data_ptr(), B, 3, H, W, cout, G.S()))
+        close(G.nchw(y), want, 2e-6 * 48 ** 0.5 * 4, "in_conv")
+    x, w, b = rnd(B, 64, 21, 130, seed=30), rnd(3, 64, 3, 3, seed=31, scale=0.05), rnd(3, seed=32)
+    want = F.conv2d(x, w, b, padding=1)
+    y = torch.empty(B, 3, 21, 130, device=cuda)
+    xg, wp, bg = G.nhwc(x).to(cuda), G.pack_weight(w.to(cuda)), b.to(cuda)
+    L.check(lib.femasr_out_conv3x3(xg.data_ptr(), wp.data_ptr(), bg.data_ptr(), y.data_ptr(), B, 21, 130, 64, G.S()))
+    close(y, want, 2e-5, "out_conv")
+
+
+def test_flip_pad_copy_window_layouts(cuda):
+    lib = L.load()
+    x = torch.rand(2, 3, 40, 24)
+    hp, wp = 48, 32
+    want = torch.cat([x, torch.flip(x, [2])], 2)[:, :, :hp, :]
+    want = torch.cat([want, torch.flip(want, [3])], 3)[:, :, :, :wp]
+    y = torch.empty(2, 3, hp, wp, device=cuda)
+    xg = x.to(cuda)
+    L.check(lib.femasr_flip_pad(xg.data_ptr(), y.data_ptr(), 2, 3, 40, 24, hp, wp, G.S()))
+    assert torch.equal(y.cpu(), want)
+    dst = torch.zeros(2, 3, 30, 30, device=cuda)
+    L.check(lib.femasr_copy_window(y.data_ptr(), dst.data_ptr(), 2, 3, hp, wp, 30, 30, 5, 7, 2, 3, 20, 11, G.S()))
+    ref = torch.zeros(2, 3, 30, 30)
+    ref[:, :, 2:22, 3:14] = want[:, :, 5:25, 7:18]
+    assert torch.equal(dst.cpu(), ref)
+    a = torch.rand(2, 5, 7, 9)
+    b = torch.empty(2, 7, 9, 5, device=cuda)
+    ag = a.to(cuda)
+    L.check(lib.femasr_nchw_to_nhwc(ag.data_ptr(), b.data_ptr(), 2, 5, 7, 9, G.S()))
+    assert torch.equal(b.cpu(), a.permute(0, 2, 3, 1))
+    c = torch.empty(2, 5, 7, 9, device=cuda)
+    L.check(lib.femasr_nhwc_to_nchw(b.data_ptr(), c.data_ptr(), 2, 5, 7, 9, G.S()))
+    assert torch.equal(c.cpu(), a)
+
+
+def test_bad_arguments_raise(cuda):
+    lib = L.load()
+    out = torch.empty(4, device=cuda)
+    assert lib.femasr_window_attention(out.data_ptr(), out.data_ptr(), out.data_ptr(), 1, 12, 8, 256, 8, 0, G.S()) == -1
+    assert lib.femasr_ln_stats(out.data_ptr(), out.data_ptr(), out.data_ptr(), 4, 128, 1e-5, G.S()) == -1
+    with pytest.raises(L.FemasrError):
+        L.check(lib.femasr_flip_pad(out.data_ptr(), out.data_ptr(), 1, 1, 4, 4, 9, 4, G.S()))
