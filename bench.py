@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py - images/sec of the FeMaSR x4 SR hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one encode_and_decode pass (`FeMaSRNet.forward`) over one batch of synthetic LR images:
+config 2 of BASELINE.json (x4, 128x128 LR, batch 32 per GPU, codebook 1024x256, random-init weights).
+With N GPUs every rank runs its own batch of 32 (weak scaling, config 4 at N=8) followed by one NCCL
+all-gather of the output shards.  Prints ONE JSON line (rank 0).
+
+  value     images/s, whole job, inputs already resident in HBM (forward [+ all-gather])
+  e2e       same metric through the public surface with HOST buffers: pinned H2D of the LR batch,
+            FeMaSRNet.forward, [all-gather], D2H of the rank's SR shard, all inside the timed region
+  roofline  the dominant kernel (implicit-GEMM conv/linear) timed per launch with CUDA events on the
+            launching stream (engine profile mode, extra steps after the timed region)
+  cpu_baseline  the CPU oracle port (the reference's ATen-CPU arithmetic) on this host's cores, bounded sample
+--impl reference runs only that CPU arm as the step and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "images/sec x4 SR 128->512 batch32"
+GFLOP_PER_IMAGE = 754.53      # algorithmic, SURVEY.md 8d / BASELINE.md section 2 (x4 128x128 forward, e256)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops_burst": d.get("bf16_tflops"), "tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_arm(args, steps: int, warmup: int, budget_s: float = 25.0):
+    """Times the CPU oracle port (ATen-CPU fp32, all host threads) on a bounded sample of the workload:
+    `sample_b` images of the same 128x128 x4 config per step.  Returns (img/s, dict)."""
+    import torch
+    from femasr_b200.spec import random_state_dict
+    from oracle import femasr_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = random_state_dict(args.scale, args.e_dim, seed=0, init="default")
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        x1 = torch.rand(1, 3, args.lr, args.lr, generator=g)
+        t0 = time.perf_counter()
+        O.encode_and_decode(sd, x1, args.scale)
+        t1 = time.perf_counter() - t0                      # also the warm-up
+        per_step_budget = budget_s / max(1, steps + warmup)
+        sample_b = int(max(1, min(args.batch, per_step_budget / max(t1, 1e-3))))
+        x = torch.rand(sample_b, 3, args.lr, args.lr, generator=g)
+        for _ in range(warmup):
+            O.encode_and_decode(sd, x, args.scale)
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            O.encode_and_decode(sd, x, args.scale)
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    ips = sample_b * steps / total
+    info = {"value": round(ips, 4), "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} steps x {sample_b} of the {args.batch} images of one batch ({args.lr}x{args.lr} LR, x{args.scale}, "
+                      f"e{args.e_dim}), oracle/femasr_oracle.py on torch-CPU fp32, {cores} threads"}
+    return ips, total / steps * 1e3, sample_b, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="LR images per GPU per step")
+    ap.add_argument("--lr", type=int, default=128)
+    ap.add_argument("--scale", type=int, default=4)
+    ap.add_argument("--e-dim", type=int, default=256)
+    ap.add_argument("--gemm-path", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"config 2: x{args.scale} SR, synthetic {args.lr}x{args.lr} LR, batch {args.batch}/GPU, codebook 1024x{args.e_dim}, "
+                "FeMaSRNet.forward (encode_and_decode), random-init weights")
+    config = {"workload": workload, "global_batch": args.batch * max(world, 1), "per_gpu_batch": args.batch,
+              "lr_size": args.lr, "scale": args.scale, "codebook": [1024, args.e_dim],
+              "parallelism": f"dp{world} (batch shards, one all-gather of outputs)" if world > 1 else "single GPU",
+              "l2": "no explicit flush: per-step working set (2.1 GB per decoder tensor at batch 32) >> 126 MB L2"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        ips, ms, sample_b, info = cpu_arm(args, args.steps, args.warmup, budget_s=60.0)
+        line = {"impl": "reference", "metric": METRIC, "value": info["value"], "unit": "images/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": info, "gpu_launches": 0,
+                "e2e": {"value": info["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    from basicsr.archs import build_network
+    from femasr_b200 import default_gemm_path
+    from femasr_b200.spec import random_state_dict
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA sm_100 device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    gemm_path = args.gemm_path if args.gemm_path is not None else default_gemm_path()
+
+    net = build_network(dict(type="FeMaSRNet", codebook_params=[[32, 1024, args.e_dim]], LQ_stage=True,
+                             scale_factor=args.scale, gemm_path=gemm_path))
+    net.load_state_dict(random_state_dict(args.scale, args.e_dim, seed=0, init="default"), strict=True)
+    net = net.to(dev).eval()
+    B, S = args.batch, args.lr
+    g = torch.Generator().manual_seed(1 + rank)
+    x_host = torch.rand(B, 3, S, S, generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+    y_host = torch.empty(B, 3, S * args.scale, S * args.scale).pin_memory()
+    gathered = torch.empty(world * B, 3, S * args.scale, S * args.scale, device=dev) if world > 1 else None
+    eng = net._native(dev)
+
+    def step_resident():
+        out = eng.forward(x_dev, want_indices=True, want_loss=True)[0]
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+        return out
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        out = net(xd)[0]                      # the public surface: FeMaSRNet.forward
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+        y_host.copy_(out, non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return ms.item()
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.last_launch_count() * args.steps
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # per-kernel CUDA-event timing (engine profile mode), 2 extra steps
+    eng.set_profile(True)
+    for _ in range(2):
+        eng.forward(x_dev)
+    prof = eng.profile()
+    eng.set_profile(False)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = load_peaks()
+    ms_step = ms_total / args.steps
+    imgs = B * world
+    value = imgs / (ms_step / 1e3)
+    e2e_value = imgs / (ms_e2e / args.steps / 1e3)
+    flops_step = eng.flops(B, S, S)
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    dname, d = dom
+    achieved = d["flops"] / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0
+    peak = peaks["tflops_sustained"] or peaks["tflops_burst"]
+    tot_ms = sum(v["ms"] for v in prof.values())
+    roofline = {"bound": "tensor", "kernel": dname, "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s",
+                "frac": round(achieved / peak, 4), "traffic": None,
+                "peak_source": peaks["source"] + ", cuBLAS bf16 sustained (kernel timed inside a long step)",
+                "launches_per_step": d["launches"] // 2, "avg_launch_ms": round(d["ms"] / max(1, d["launches"]), 4),
+                "share_of_step": round(d["ms"] / tot_ms, 4) if tot_ms else None,
+                "flops_counted": "algorithmic 2*MAC of the convs/linears this kernel executed",
+                "arithmetic": "fp32 FFMA (SIMT)" if gemm_path == 0 else "tcgen05 kind::f16, 3-MMA split-fp16 (hi*hi+hi*lo+lo*hi), fp32 accumulate in TMEM",
+                "path_tflops": round(flops_step / (ms_step / 1e3) / 1e12, 2),
+                "path_frac": round(flops_step / (ms_step / 1e3) / 1e12 / peak, 4),
+                "kernels": {k: {"launches": v["launches"] // 2, "ms_per_step": round(v["ms"] / 2, 3)} for k, v in prof.items()}}
+    line = {"metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "gflop_per_image": round(flops_step / B / 1e9, 2), "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": y_host.numel() * 4,
+                    "note": "FeMaSRNet.forward on a pinned-host batch: H2D + forward (+ all-gather) + D2H of the rank's SR shard"},
+            "roofline": roofline}
+    if not args.no_cpu_baseline and world == 1:
+        _, _, _, info = cpu_arm(args, steps=2, warmup=0, budget_s=20.0)
+        line["cpu_baseline"] = info
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -78,6 +78,8 @@ struct ParamInfo {
 
 struct Tap { float* dst; size_t cap; };
 
+struct ProfRec { const char* name; double flops; cudaEvent_t e0, e1; };
+
 }  // namespace femasr
 
 using namespace femasr;
@@ -92,7 +94,11 @@ struct femasr_net {
   DevBuf esq;
   std::map<std::string, Tap> taps;
   int last_launches = 0;
+  bool profile = false;
+  std::vector<ProfRec> prof;
+  std::string prof_json;
   ~femasr_net() {
+    for (auto& r : prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto& kv : raw) cudaFree(kv.second.p);
     for (auto& kv : packed) cudaFree(kv.second.p);
     for (auto& kv : tcw) cudaFree(kv.second.p);
@@ -176,6 +182,22 @@ struct Ctx {
   bool ok() const { return status == FEMASR_OK; }
   void check(int s) { if (status == FEMASR_OK && s != FEMASR_OK) status = s; }
 
+  // every kernel launch of the graph goes through here; in profile mode it is bracketed by CUDA events
+  template <class F>
+  void run(const char* name, double flops, F&& f) {
+    if (dry() || !ok()) return;
+    if (net->profile) {
+      ProfRec r{name, flops, nullptr, nullptr};
+      cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+      cudaEventRecord(r.e0, st);
+      check(f());
+      cudaEventRecord(r.e1, st);
+      net->prof.push_back(r);
+    } else {
+      check(f());
+    }
+  }
+
   const float* P(const std::string& name) {      // packed (or raw when there is no packed form)
     if (dry()) return nullptr;
     auto it = net->packed.find(name);
@@ -209,13 +231,19 @@ struct Ctx {
     a.B = B; a.Hin = Hin; a.Win = Win; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.stride = stride;
     a.upsample = upsample; a.prologue = prologue; a.act = act;
     if (!ok()) return;
-    check(femasr_igemm_simt(&a, st));
+    int Ho, Wo;
+    if (ksize == 1) { Ho = Hin; Wo = Win; }
+    else { const int He = upsample ? 2 * Hin : Hin, We = upsample ? 2 * Win : Win;
+           Ho = stride == 1 ? He : (He - 1) / 2 + 1; Wo = stride == 1 ? We : (We - 1) / 2 + 1; }
+    const double flops = 2.0 * B * Ho * Wo * (double)Cout * Cin * ksize * ksize;
+    run("igemm_simt", flops, [&] { return femasr_igemm_simt(&a, st); });
   }
 
   // GroupNorm statistics of x folded into scale/shift tables (allocated by the caller)
   void gn(const std::string& norm, const float* x, float* sc, float* sh, float* scratch, int B, int HW, int C) {
     if (dry() || !ok()) return;
-    check(femasr_gn_stats(x, P(norm + ".weight"), P(norm + ".bias"), sc, sh, scratch, B, HW, C, 1e-6f, st));
+    const float *gw = P(norm + ".weight"), *gb = P(norm + ".bias");
+    run("gn_stats", 0.0, [&] { return femasr_gn_stats(x, gw, gb, sc, sh, scratch, B, HW, C, 1e-6f, st); });
   }
 
   // fema_utils.py:65-84, in place on x; optional extra residual added after the block (encoder skip).
@@ -257,14 +285,16 @@ struct Ctx {
       for (int b = 0; b < 6; ++b) {
         const std::string bp = rp + ".residual_group.blocks." + std::to_string(b);
         const float* in = b == 0 ? X : T;
-        if (!dry() && ok()) check(femasr_ln_stats(in, mu, rs, (int)M, C, 1e-5f, st));
+        run("ln_stats", 0.0, [&] { return femasr_ln_stats(in, mu, rs, (int)M, C, 1e-5f, st); });
         conv(bp + ".attn.qkv", in, qkv, B, H, W, C, 3 * C, 1, 1, 0, FEMASR_PRO_LN, mu, rs, P(bp + ".norm1.weight"),
              P(bp + ".norm1.bias"), 0, nullptr, nullptr);
-        if (!dry() && ok())
-          check(femasr_window_attention(qkv, P(bp + ".attn.relative_position_bias_table"), ao, B, H, W, C, 8,
-                                        (b & 1) ? 4 : 0, st));
+        {
+          const float* rb = P(bp + ".attn.relative_position_bias_table");
+          run("window_attention", 2.0 * 2.0 * 64 * C * (double)M,
+              [&] { return femasr_window_attention(qkv, rb, ao, B, H, W, C, 8, (b & 1) ? 4 : 0, st); });
+        }
         conv(bp + ".attn.proj", ao, T, B, H, W, C, C, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, in, nullptr);
-        if (!dry() && ok()) check(femasr_ln_stats(T, mu, rs, (int)M, C, 1e-5f, st));
+        run("ln_stats", 0.0, [&] { return femasr_ln_stats(T, mu, rs, (int)M, C, 1e-5f, st); });
         conv(bp + ".mlp.fc1", T, hid, B, H, W, C, 4 * C, 1, 1, 0, FEMASR_PRO_LN, mu, rs, P(bp + ".norm2.weight"),
              P(bp + ".norm2.bias"), FEMASR_ACT_GELU, nullptr, nullptr);
         conv(bp + ".mlp.fc2", hid, T, B, H, W, 4 * C, C, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, T, nullptr);
@@ -289,8 +319,11 @@ struct Ctx {
     float* d2 = up_block("decoder_group.2.block.1", "decoder_group.2.block.2", "decoder_group.2.block.3", d1, B, 4 * h, 4 * w, 128, 64, nullptr);
     ar.release(d1);
     tap("dec2", d2, (size_t)B * 8 * h * 8 * w * 64);
-    if (!dry() && ok())
-      check(femasr_out_conv3x3(d2, P("out_conv.weight"), P("out_conv.bias"), y_nchw, B, 8 * h, 8 * w, 64, st));
+    {
+      const float *ow = P("out_conv.weight"), *ob = P("out_conv.bias");
+      run("out_conv", 2.0 * 9 * 64 * 3 * (double)B * 64 * h * w,
+          [&] { return femasr_out_conv3x3(d2, ow, ob, y_nchw, B, 8 * h, 8 * w, 64, st); });
+    }
     ar.release(d2);
   }
 
@@ -301,8 +334,12 @@ struct Ctx {
     int c = chan(256 / cfg.scale_factor);
     int h = H - 1, w = W - 1;
     float* cur = ar.alloc((size_t)B * h * w * c);
-    if (!dry() && ok())
-      check(femasr_in_conv4x4(x_nchw, P(enc + ".in_conv.weight"), P(enc + ".in_conv.bias"), cur, B, cfg.in_channel, H, W, c, st));
+    {
+      const float *iw = P(enc + ".in_conv.weight"), *ib = P(enc + ".in_conv.bias");
+      const int c0 = c;
+      run("in_conv", 2.0 * 16 * cfg.in_channel * c0 * (double)B * h * w,
+          [&] { return femasr_in_conv4x4(x_nchw, iw, ib, cur, B, cfg.in_channel, H, W, c0, st); });
+    }
     tap("in_conv", cur, (size_t)B * h * w * c);
     for (int i = 0; i < d; ++i) {
       const std::string b = enc + ".blocks." + std::to_string(i);
@@ -336,9 +373,9 @@ struct Ctx {
     float* zq = ar.alloc(N * e);
     float* lrows = ar.alloc(N);
     if (!dry() && ok()) {
-      check(femasr_vq_select(z, zc, net->raw["quantize_group.0.embedding.weight"].p, net->esq.p, indices, zq, lrows,
-                             (int)N, cfg.n_e, e, 0, st));
-      if (cb_loss && ok()) check(femasr_sum_scaled(lrows, cb_loss, N, 1.25 / ((double)N * e), st));
+      const float* cbw = net->raw["quantize_group.0.embedding.weight"].p;
+      run("vq_select", 0.0, [&] { return femasr_vq_select(z, zc, cbw, net->esq.p, indices, zq, lrows, (int)N, cfg.n_e, e, 0, st); });
+      if (cb_loss) run("sum_scaled", 0.0, [&] { return femasr_sum_scaled(lrows, cb_loss, N, 1.25 / ((double)N * e), st); });
     }
     ar.release(lrows);
     ar.release(zc);
@@ -354,8 +391,10 @@ struct Ctx {
     const int e = net->cfg.e_dim;
     const size_t N = (size_t)B * h * w;
     float* zq = ar.alloc(N * e);
-    if (!dry() && ok())
-      check(femasr_codebook_gather(idx, net->raw["quantize_group.0.embedding.weight"].p, zq, (int)N, net->cfg.n_e, e, st));
+    if (!dry() && ok()) {
+      const float* cbw = net->raw["quantize_group.0.embedding.weight"].p;
+      run("codebook_gather", 0.0, [&] { return femasr_codebook_gather(idx, cbw, zq, (int)N, net->cfg.n_e, e, st); });
+    }
     decode(zq, y_nchw, B, h, w, nullptr, nullptr);
     ar.release(zq);
   }
@@ -511,6 +550,40 @@ extern "C" int femasr_net_set_tap(femasr_net* net, const char* stage, float* dst
 }
 
 extern "C" int femasr_net_last_launch_count(femasr_net* net) { return net ? net->last_launches : 0; }
+
+extern "C" int femasr_net_set_profile(femasr_net* net, int enable) {
+  FEMASR_CHECK_ARG(net, "set_profile: null");
+  for (auto& r : net->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  net->prof.clear();
+  net->profile = enable != 0;
+  return FEMASR_OK;
+}
+
+// JSON {"kernel": {"launches": n, "ms": total, "flops": total}, ...} of the launches recorded since
+// femasr_net_set_profile(net, 1).  Synchronises on the recorded events.
+extern "C" const char* femasr_net_profile_json(femasr_net* net) {
+  if (!net) return "{}";
+  struct Agg { long n = 0; double ms = 0, flops = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : net->prof) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess || cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+    Agg& a = agg[r.name];
+    a.n += 1; a.ms += ms; a.flops += r.flops;
+  }
+  std::string js = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f, \"flops\": %.6e}", first ? "" : ", ",
+             kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops);
+    js += buf;
+    first = false;
+  }
+  js += "}";
+  net->prof_json = js;
+  return net->prof_json.c_str();
+}
 
 extern "C" double femasr_net_flops(femasr_net* net, int B, int H, int W) {
   if (!net) return 0.0;

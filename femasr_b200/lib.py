@@ -54,6 +54,8 @@ SIGNATURES = {
     "femasr_net_decode_workspace_bytes": (_I, [_V, _I, _I, _I, C.POINTER(_Z)]),
     "femasr_net_set_tap": (_I, [_V, C.c_char_p, _V, _Z]),
     "femasr_net_last_launch_count": (_I, [_V]),
+    "femasr_net_set_profile": (_I, [_V, _I]),
+    "femasr_net_profile_json": (C.c_char_p, [_V]),
     "femasr_net_flops": (_D, [_V, _I, _I, _I]),
     "femasr_flip_pad": (_I, [_V, _V, _I, _I, _I, _I, _I, _I, _V]),
     "femasr_copy_window": (_I, [_V, _V] + [_I] * 12 + [_V]),

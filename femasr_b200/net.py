@@ -177,6 +177,14 @@ class NativeNet:
                                                        ws.data_ptr(), ws.numel(), _stream()))
         return y
 
+    def set_profile(self, enable: bool):
+        L.check(self.lib.femasr_net_set_profile(self._h, int(enable)))
+
+    def profile(self) -> dict:
+        """{kernel: {launches, ms, flops}} of the launches since set_profile(True) (CUDA-event timed)."""
+        import json
+        return json.loads(self.lib.femasr_net_profile_json(self._h).decode())
+
     def last_launch_count(self) -> int:
         return int(self.lib.femasr_net_last_launch_count(self._h))
 

@@ -86,6 +86,11 @@ int femasr_net_decode_workspace_bytes(femasr_net* net, int B, int h, int w, size
 int femasr_net_set_tap(femasr_net* net, const char* stage, float* dst, size_t capacity);
 /* Number of kernels the last femasr_net_forward launched (bench.py's gpu_launches). */
 int femasr_net_last_launch_count(femasr_net* net);
+/* Per-kernel timing for bench.py's roofline: while enabled, every launch of femasr_net_forward is
+ * bracketed by CUDA events on the launching stream; femasr_net_profile_json returns
+ * {"kernel": {"launches": n, "ms": total, "flops": algorithmic total}, ...} (valid until the next call). */
+int femasr_net_set_profile(femasr_net* net, int enable);
+const char* femasr_net_profile_json(femasr_net* net);
 /* Algorithmic FLOPs (2*MAC, conv+linear+QK/PV+VQ distance) of one forward on [B,3,H,W]. */
 double femasr_net_flops(femasr_net* net, int B, int H, int W);
 
