@@ -223,6 +223,10 @@ struct Ctx {
   void conv(const std::string& wname, const float* x, float* y, int B, int Hin, int Win, int Cin, int Cout, int ksize,
             int stride, int upsample, int prologue, const float* pa, const float* pb, const float* gamma,
             const float* beta, int act, const float* res1, const float* res2, bool has_bias = true) {
+    if (has_bias && tc_eligible(wname, Cin, Cout, ksize, stride)) {
+      conv_tc(wname, x, y, B, Hin, Win, Cin, Cout, ksize, upsample, prologue, pa, pb, gamma, beta, act, res1, res2);
+      return;
+    }
     if (dry() || !ok()) return;
     femasr_igemm_args a;
     memset(&a, 0, sizeof(a));
@@ -237,6 +241,36 @@ struct Ctx {
            Ho = stride == 1 ? He : (He - 1) / 2 + 1; Wo = stride == 1 ? We : (We - 1) / 2 + 1; }
     const double flops = 2.0 * B * Ho * Wo * (double)Cout * Cin * ksize * ksize;
     run("igemm_simt", flops, [&] { return femasr_igemm_simt(&a, st); });
+  }
+
+  bool tc_eligible(const std::string& wname, int Cin, int Cout, int ksize, int stride) const {
+    return net->cfg.gemm_path == 1 && stride == 1 && (ksize == 1 || ksize == 3) && Cin % 64 == 0 && Cout % 64 == 0 &&
+           (dry() || net->tcw.count(wname + ".weight") != 0);
+  }
+
+  // tensor-core variant of conv(): stage the activation operand (prologue + upsample + fp16 split), then the
+  // tcgen05 implicit GEMM.  Allocation happens in dry runs too so the workspace size is exact.
+  void conv_tc(const std::string& wname, const float* x, float* y, int B, int Hin, int Win, int Cin, int Cout, int ksize,
+               int upsample, int prologue, const float* pa, const float* pb, const float* gamma, const float* beta,
+               int act, const float* res1, const float* res2) {
+    const int Hc = upsample ? 2 * Hin : Hin, Wc = upsample ? 2 * Win : Win;
+    const size_t plane_halves = (size_t)B * Hc * Wc * Cin;
+    float* ahi = ar.alloc((plane_halves + 1) / 2);
+    float* alo = ar.alloc((plane_halves + 1) / 2);
+    if (!dry() && ok()) {
+      run("tc_prepare", 0.0, [&] {
+        return femasr_tc_prepare(x, ahi, alo, prologue, pa, pb, gamma, beta, B, Hin, Win, Cin, upsample,
+                                 prologue == FEMASR_PRO_LN ? 1e-5f : 1e-6f, st);
+      });
+      femasr_tc_args t;
+      memset(&t, 0, sizeof(t));
+      t.a_hi = ahi; t.a_lo = alo; t.w_blob = net->tcw[wname + ".weight"].p; t.bias = P(wname + ".bias");
+      t.res1 = res1; t.res2 = res2; t.y = y; t.B = B; t.H = Hc; t.W = Wc; t.Cin = Cin; t.Cout = Cout;
+      t.ksize = ksize; t.act = act;
+      const double flops = 2.0 * B * Hc * Wc * (double)Cout * Cin * ksize * ksize;
+      run("tc_igemm", flops, [&] { return femasr_tc_igemm(&t, st); });
+    }
+    ar.release(alo); ar.release(ahi);
   }
 
   // GroupNorm statistics of x folded into scale/shift tables (allocated by the caller)
@@ -280,12 +314,13 @@ struct Ctx {
     float* hid = ar.alloc(M * 4 * C);
     float* mu = ar.alloc(M);
     float* rs = ar.alloc(M);
+    const bool tc = net->cfg.gemm_path == 1;   // the tensor-core operand staging computes LayerNorm itself
     for (int r = 0; r < 4; ++r) {
       const std::string rp = p + ".swin_blks." + std::to_string(r);
       for (int b = 0; b < 6; ++b) {
         const std::string bp = rp + ".residual_group.blocks." + std::to_string(b);
         const float* in = b == 0 ? X : T;
-        run("ln_stats", 0.0, [&] { return femasr_ln_stats(in, mu, rs, (int)M, C, 1e-5f, st); });
+        if (!tc) run("ln_stats", 0.0, [&] { return femasr_ln_stats(in, mu, rs, (int)M, C, 1e-5f, st); });
         conv(bp + ".attn.qkv", in, qkv, B, H, W, C, 3 * C, 1, 1, 0, FEMASR_PRO_LN, mu, rs, P(bp + ".norm1.weight"),
              P(bp + ".norm1.bias"), 0, nullptr, nullptr);
         {
@@ -294,7 +329,7 @@ struct Ctx {
               [&] { return femasr_window_attention(qkv, rb, ao, B, H, W, C, 8, (b & 1) ? 4 : 0, st); });
         }
         conv(bp + ".attn.proj", ao, T, B, H, W, C, C, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, in, nullptr);
-        run("ln_stats", 0.0, [&] { return femasr_ln_stats(T, mu, rs, (int)M, C, 1e-5f, st); });
+        if (!tc) run("ln_stats", 0.0, [&] { return femasr_ln_stats(T, mu, rs, (int)M, C, 1e-5f, st); });
         conv(bp + ".mlp.fc1", T, hid, B, H, W, C, 4 * C, 1, 1, 0, FEMASR_PRO_LN, mu, rs, P(bp + ".norm2.weight"),
              P(bp + ".norm2.bias"), FEMASR_ACT_GELU, nullptr, nullptr);
         conv(bp + ".mlp.fc2", hid, T, B, H, W, 4 * C, C, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, T, nullptr);
@@ -457,7 +492,15 @@ extern "C" int femasr_net_set_param(femasr_net* net, const char* name, const flo
   if (pi.kind == 1) {
     DevBuf& pb = net->packed[key];
     if (!pb.p) { FEMASR_CUDA(cudaMalloc(&pb.p, numel * sizeof(float))); pb.n = numel; }
-    return femasr_pack_weight(rb.p, pb.p, pi.Cout, pi.Cin, pi.k, pi.k, st);
+    int s = femasr_pack_weight(rb.p, pb.p, pi.Cout, pi.Cin, pi.k, pi.k, st);
+    if (s) return s;
+    if (net->cfg.gemm_path == 1 && (pi.k == 1 || pi.k == 3) && pi.Cin % 64 == 0 && pi.Cout % 64 == 0) {
+      DevBuf& tb = net->tcw[key];
+      const size_t bytes = femasr_tc_weight_bytes(pi.Cout, pi.Cin, pi.k, pi.k);
+      if (!tb.p) { FEMASR_CUDA(cudaMalloc(&tb.p, bytes)); tb.n = bytes / sizeof(float); }
+      return femasr_tc_pack_weight(rb.p, tb.p, pi.Cout, pi.Cin, pi.k, pi.k, st);
+    }
+    return FEMASR_OK;
   }
   if (pi.kind == 2) {
     DevBuf& pb = net->packed[key];

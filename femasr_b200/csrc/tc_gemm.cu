@@ -1,0 +1,564 @@
+// tcgen05 tensor-core implicit GEMM (3x3 stride-1 convolution and linear layers) for sm_100a, with
+// fp32-grade accuracy from a two-term fp16 operand split:
+//
+//     a = a_hi + a_lo,  w*2^s = w_hi + w_lo          (fp16, 11-bit significands each)
+//     D = a_hi*w_hi + a_hi*w_lo + a_lo*w_hi          (3 tcgen05.mma kind::f16 per k-step, fp32 accumulate in TMEM)
+//
+// i.e. ~22 significand bits per operand; the dropped a_lo*w_lo term is ~2^-22 relative (SURVEY 7.3-1:
+// the path needs >=18 bits before the VQ and >=13 after it; single-pass fp16/bf16/tf32 fails parity).
+//
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0  TMA producer: activation tile = 4-D box (64 ch x Wt x Ht x 1) of the NHWC fp16 planes at the
+//           tap offset (kh-1, kw-1) - out-of-bounds rows/cols are zero-filled by TMA, which IS the conv
+//           padding - and the weight tile = 2-D box (64 x BN) of the K-major fp16 planes; 128B swizzle.
+//   warp 1  MMA issuer (one elected thread): 4 k-steps x 3 split products per 64-wide k-block into a
+//           128 x BN fp32 accumulator in TMEM (two accumulators: the epilogue of tile i overlaps tile i+1).
+//   warp 2  TMEM allocator.
+//   warps 4-7  epilogue: tcgen05.ld 32 columns at a time -> *2^-s + bias -> GELU -> + residual(s) -> fp32 NHWC.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+
+namespace femasr {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug must not hang the GPU; after 4 s the kernel traps (reported as a
+// CUDA error by the next API call) instead of spinning forever.
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xFFFu) == 0 && global_ns() - t0 > 4000000000ull) {   // 4 s: far beyond any legitimate wait
+      printf("femasr tc_gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile ([rows][64 fp16], 8-row atoms of 1024 B): SBO = 1024 B, LBO unused (=1),
+// descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  cute::UMMA::SmemDescriptor bit layout.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+struct TcP {
+  const float* bias; const float* res1; const float* res2; float* y; const float* inv_scale;
+  int B, H, W, Cin, Cout, taps, act;
+  int Wt, Ht, wt_shift;          // 128-pixel tile = Ht rows x Wt cols (Wt power of two)
+  int tiles_x, tiles_y, n_tiles; // per image spatial tiles, Cout / BN
+  int num_tiles, cchunks;        // total tiles, Cin / 64
+};
+
+constexpr int TC_BM = 128, TC_BK = 64;
+constexpr int A_PLANE_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+
+template <int BN>
+struct TcCfg {
+  static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * BN * TC_BK * 2;
+  static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators; power of two for BN in {64,128,256}
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcP p) {
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base pointer
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int nkb = p.taps * p.cchunks;
+  const int ksz = p.taps == 9 ? 3 : 1;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      int mt = tile / p.n_tiles;
+      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int b = mt / p.tiles_y;
+      const int x0 = tx * p.Wt, y0 = ty * p.Ht, n0 = nt * BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int tap = kb / p.cchunks;
+        const int c0 = (kb - tap * p.cchunks) * TC_BK;
+        const int kh = tap / ksz, kw = tap - kh * ksz;
+        const int pad = ksz == 3 ? 1 : 0;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+        mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+        tma_load_4d(sa, &map_a_hi, full_bar(stage), c0, x0 + kw - pad, y0 + kh - pad, b);
+        tma_load_4d(sa + A_PLANE_BYTES, &map_a_lo, full_bar(stage), c0, x0 + kw - pad, y0 + kh - pad, b);
+        tma_load_2d(sa + 2 * A_PLANE_BYTES, &map_b_hi, full_bar(stage), tap * p.Cin + c0, n0);
+        tma_load_2d(sa + 2 * A_PLANE_BYTES + BN * TC_BK * 2, &map_b_lo, full_bar(stage), tap * p.Cin + c0, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major both,
+    // N>>3 at bits 17-22, M>>4 at bits 24-28.
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+        const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + A_PLANE_BYTES);
+        const uint64_t b_hi = make_sw128_desc(sa + 2 * A_PLANE_BYTES);
+        const uint64_t b_lo = make_sw128_desc(sa + 2 * A_PLANE_BYTES + BN * TC_BK * 2);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint64_t ko = (uint64_t)((k * 32) >> 4);   // +32 bytes per k-step inside the 128B swizzle atom
+          // small cross terms first, the dominant hi*hi product last
+          umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+          umma_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+        }
+        umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;                    // TMEM lane quarter of this warp (warp_id % 4)
+    const int row = ew * 32 + lane;
+    const float inv_scale = __ldg(p.inv_scale);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      int mt = tile / p.n_tiles;
+      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int b = mt / p.tiles_y;
+      const int y = ty * p.Ht + (row >> p.wt_shift), x = tx * p.Wt + (row & (p.Wt - 1));
+      const bool valid = y < p.H && x < p.W;
+      const long off = (((long)b * p.H + y) * p.W + x) * p.Cout + nt * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + (uint32_t)c, r);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = __uint_as_float(r[j]) * inv_scale; o.y = __uint_as_float(r[j + 1]) * inv_scale;
+            o.z = __uint_as_float(r[j + 2]) * inv_scale; o.w = __uint_as_float(r[j + 3]) * inv_scale;
+            if (p.bias) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nt * BN + c + j));
+              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+            }
+            if (p.act == FEMASR_ACT_GELU) { o.x = gelu_erf_f(o.x); o.y = gelu_erf_f(o.y); o.z = gelu_erf_f(o.z); o.w = gelu_erf_f(o.w); }
+            if (p.res1) {
+              const float4 rv = *reinterpret_cast<const float4*>(p.res1 + off + c + j);
+              o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+            }
+            if (p.res2) {
+              const float4 rv = *reinterpret_cast<const float4*>(p.res2 + off + c + j);
+              o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+            }
+            *reinterpret_cast<float4*>(p.y + off + c + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));             // 128 arrivals release the accumulator
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ operand preparation
+__device__ __forceinline__ void split_store8(const float (&v)[8], __half* hi, __half* lo) {
+  __align__(16) __half h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float c = fminf(fmaxf(v[i], -65504.f), 65504.f);
+    h[i] = __float2half_rn(c);
+    l[i] = __float2half_rn(c - __half2float(h[i]));
+  }
+  *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(h);
+  *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(l);
+}
+
+// x fp32 NHWC [B,H,W,C] -> fp16 hi/lo planes [B,H*up,W*up,C] with an optional GroupNorm+SiLU transform
+// (scale/shift tables [B,C]) and optional nearest x2 replication.  8 channels per thread.
+template <int MODE>
+__global__ void __launch_bounds__(256) tc_prepare_kernel(const float* __restrict__ x, __half* __restrict__ hi,
+                                                         __half* __restrict__ lo, const float* __restrict__ sc,
+                                                         const float* __restrict__ sh, int H, int W, int C, int up,
+                                                         long total8) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int c8 = C / 8;
+  const int cq = (int)(i % c8);
+  const long pix = i / c8;
+  const int xw = (int)(pix % W);
+  const long t = pix / W;
+  const int yh = (int)(t % H);
+  const int b = (int)(t / H);
+  const float4* src = reinterpret_cast<const float4*>(x + pix * C + cq * 8);
+  const float4 a = __ldg(src), bq = __ldg(src + 1);
+  float v[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+  if (MODE == FEMASR_PRO_GN_SILU) {
+    const float4* ps = reinterpret_cast<const float4*>(sc + (long)b * C + cq * 8);
+    const float4* pt = reinterpret_cast<const float4*>(sh + (long)b * C + cq * 8);
+    const float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), t0 = __ldg(pt), t1 = __ldg(pt + 1);
+    const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = silu_f(fmaf(v[k], s[k], tt[k]));
+  }
+  if (!up) {
+    split_store8(v, hi + pix * C + cq * 8, lo + pix * C + cq * 8);
+  } else {
+    const int W2 = 2 * W;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const long op = (((long)b * 2 * H + 2 * yh + dy) * W2 + 2 * xw + dx) * C + cq * 8;
+        split_store8(v, hi + op, lo + op);
+      }
+  }
+}
+
+// LayerNorm (C = 256, eps) fused with the split: one warp per token row.
+__global__ void __launch_bounds__(256) tc_prepare_ln_kernel(const float* __restrict__ x, __half* __restrict__ hi,
+                                                            __half* __restrict__ lo, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, long M, float eps) {
+  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float4* r = reinterpret_cast<const float4*>(x + row * 256 + lane * 8);
+  const float4 a = __ldg(r), b = __ldg(r + 1);
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+  s = warp_sum(s);
+  const float mu = s * (1.0f / 256.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { const float d = v[k] - mu; q = fmaf(d, d, q); }
+  q = warp_sum(q) * (1.0f / 256.0f);
+  const float rs = 1.0f / sqrtf(q + eps);
+  const float4* pg = reinterpret_cast<const float4*>(gamma + lane * 8);
+  const float4* pb = reinterpret_cast<const float4*>(beta + lane * 8);
+  const float4 g0 = __ldg(pg), g1 = __ldg(pg + 1), b0 = __ldg(pb), b1 = __ldg(pb + 1);
+  const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = (v[k] - mu) * rs * g[k] + be[k];
+  split_store8(v, hi + row * 256 + lane * 8, lo + row * 256 + lane * 8);
+}
+
+// weights: OIHW fp32 -> [Cout][taps*Cin] fp16 hi/lo planes of w * 2^s, s chosen so max|w|*2^s is in [512,1024)
+__global__ void absmax_kernel(const float* __restrict__ w, unsigned int* __restrict__ out, long n) {
+  float m = 0.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order like uints
+}
+__global__ void tc_pack_weight_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo,
+                                      const unsigned int* __restrict__ absmax, float* __restrict__ inv_scale, int Cout,
+                                      int Cin, int KH, int KW) {
+  const float mx = __uint_as_float(*absmax);
+  int ex = 0;
+  if (mx > 0.f) frexpf(mx, &ex);          // mx = f * 2^ex, f in [0.5,1)
+  const int s = mx > 0.f ? 10 - ex : 0;   // mx * 2^s in [512, 1024)
+  const float scale = ldexpf(1.0f, s);
+  const long n = (long)Cout * Cin * KH * KW;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *inv_scale = ldexpf(1.0f, -s);
+  if (i >= n) return;
+  // i indexes the packed layout [co][(kh*KW+kw)*Cin + ci]
+  const long K = (long)Cin * KH * KW;
+  const int co = (int)(i / K);
+  const long k = i - (long)co * K;
+  const int tap = (int)(k / Cin), ci = (int)(k - (long)tap * Cin);
+  const int kh = tap / KW, kw = tap - kh * KW;
+  const float v = w[(((long)co * Cin + ci) * KH + kh) * KW + kw] * scale;   // exact (power of two)
+  const __half h = __float2half_rn(v);
+  hi[i] = h;
+  lo[i] = __float2half_rn(v - __half2float(h));
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                    const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(FEMASR_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FEMASR_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return FEMASR_OK;
+}
+
+static int g_sm_count = 0;
+static int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+template <int BN>
+static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                     const TcP& p, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FEMASR_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  tc_igemm_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
+  return launch_status("tc_igemm_kernel");
+}
+
+}  // namespace femasr
+
+using namespace femasr;
+
+extern "C" size_t femasr_tc_weight_bytes(int Cout, int Cin, int kh, int kw) {
+  return (size_t)2 * Cout * Cin * kh * kw * sizeof(__half) + 256;   // hi plane, lo plane, then {absmax, inv_scale}
+}
+
+// Layout of the packed tensor-core weight blob: [hi plane][lo plane][uint absmax][float inv_scale] (see above).
+extern "C" int femasr_tc_pack_weight(const float* w_oihw, void* blob, int Cout, int Cin, int kh, int kw, void* stream) {
+  FEMASR_CHECK_ARG(w_oihw && blob && Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "tc_pack_weight: bad argument");
+  const long n = (long)Cout * Cin * kh * kw;
+  __half* hi = reinterpret_cast<__half*>(blob);
+  __half* lo = hi + n;
+  unsigned int* amax = reinterpret_cast<unsigned int*>(lo + n);
+  float* inv = reinterpret_cast<float*>(amax + 1);
+  cudaStream_t st = as_stream(stream);
+  FEMASR_CUDA(cudaMemsetAsync(amax, 0, 8, st));
+  absmax_kernel<<<(unsigned)std::min<long>(cdiv(n, 256), 1024), 256, 0, st>>>(w_oihw, amax, n);
+  int s = launch_status("absmax_kernel");
+  if (s) return s;
+  tc_pack_weight_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(w_oihw, hi, lo, amax, inv, Cout, Cin, kh, kw);
+  return launch_status("tc_pack_weight_kernel");
+}
+
+extern "C" int femasr_tc_prepare(const float* x, void* a_hi, void* a_lo, int mode, const float* pro_a, const float* pro_b,
+                                 const float* gamma, const float* beta, int B, int H, int W, int C, int upsample,
+                                 float eps, void* stream) {
+  FEMASR_CHECK_ARG(x && a_hi && a_lo && B > 0 && H > 0 && W > 0, "tc_prepare: bad argument");
+  FEMASR_CHECK_ARG(C % 8 == 0, "tc_prepare: C must be a multiple of 8");
+  cudaStream_t st = as_stream(stream);
+  __half* hi = reinterpret_cast<__half*>(a_hi);
+  __half* lo = reinterpret_cast<__half*>(a_lo);
+  if (mode == FEMASR_PRO_LN) {
+    FEMASR_CHECK_ARG(C == 256 && gamma && beta && !upsample, "tc_prepare: LN mode needs C=256, gamma/beta, no upsample");
+    const long M = (long)B * H * W;
+    tc_prepare_ln_kernel<<<(unsigned)cdiv(M, 8), 256, 0, st>>>(x, hi, lo, gamma, beta, M, eps);
+    return launch_status("tc_prepare_ln_kernel");
+  }
+  const long total8 = (long)B * H * W * (C / 8);
+  const unsigned grid = (unsigned)cdiv(total8, 256);
+  if (mode == FEMASR_PRO_GN_SILU) {
+    FEMASR_CHECK_ARG(pro_a && pro_b, "tc_prepare: GN mode needs the scale/shift tables");
+    tc_prepare_kernel<FEMASR_PRO_GN_SILU><<<grid, 256, 0, st>>>(x, hi, lo, pro_a, pro_b, H, W, C, upsample, total8);
+  } else if (mode == FEMASR_PRO_NONE) {
+    tc_prepare_kernel<FEMASR_PRO_NONE><<<grid, 256, 0, st>>>(x, hi, lo, nullptr, nullptr, H, W, C, upsample, total8);
+  } else {
+    return fail(FEMASR_ERR_ARG, "tc_prepare: bad mode");
+  }
+  return launch_status("tc_prepare_kernel");
+}
+
+// y = act(conv(a) + bias) + res1 + res2 with a given as fp16 hi/lo planes at the conv-input resolution.
+extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
+  FEMASR_CHECK_ARG(a && a->a_hi && a->a_lo && a->w_blob && a->y, "tc_igemm: null pointer");
+  FEMASR_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0, "tc_igemm: empty input");
+  FEMASR_CHECK_ARG(a->ksize == 1 || a->ksize == 3, "tc_igemm: ksize must be 1 or 3");
+  FEMASR_CHECK_ARG(a->Cin % 64 == 0 && a->Cout % 64 == 0, "tc_igemm: Cin and Cout must be multiples of 64");
+  int B = a->B, H = a->H, W = a->W;
+  if (a->ksize == 1) { W = B * H * W; H = 1; B = 1; }     // pointwise: one long row of tokens
+  FEMASR_CHECK_ARG((long)W < (1l << 31), "tc_igemm: too many rows");
+  const int taps = a->ksize * a->ksize;
+  const long Ktot = (long)taps * a->Cin;
+  const long nw = (long)a->Cout * Ktot;
+  const __half* w_hi = reinterpret_cast<const __half*>(a->w_blob);
+  const __half* w_lo = w_hi + nw;
+  const float* inv_scale = reinterpret_cast<const float*>(reinterpret_cast<const unsigned int*>(w_lo + nw) + 1);
+
+  TcP p;
+  p.bias = a->bias; p.res1 = a->res1; p.res2 = a->res2; p.y = a->y; p.inv_scale = inv_scale;
+  p.B = B; p.H = H; p.W = W; p.Cin = a->Cin; p.Cout = a->Cout; p.taps = taps; p.act = a->act;
+  // tile shape: the widest power-of-two Wt <= 128 that wastes the fewest padded pixels
+  int best_wt = 8; long best_cost = -1;
+  for (int wt = 128; wt >= 8; wt >>= 1) {
+    const int ht = 128 / wt;
+    const long cost = cdiv(W, wt) * wt * cdiv(H, ht) * ht;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_wt = wt; }
+  }
+  p.Wt = best_wt; p.Ht = 128 / best_wt;
+  p.wt_shift = 0; while ((1 << p.wt_shift) < p.Wt) ++p.wt_shift;
+  p.tiles_x = (int)cdiv(W, p.Wt); p.tiles_y = (int)cdiv(H, p.Ht);
+  const int BN = a->Cout % 256 == 0 ? 256 : (a->Cout % 128 == 0 ? 128 : 64);
+  p.n_tiles = a->Cout / BN;
+  const long ntile = (long)B * p.tiles_x * p.tiles_y * p.n_tiles;
+  FEMASR_CHECK_ARG(ntile < (1l << 31), "tc_igemm: too many tiles");
+  p.num_tiles = (int)ntile; p.cchunks = a->Cin / 64;
+
+  CUtensorMap mah, mal, mbh, mbl;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t str[3] = {(cuuint64_t)a->Cin * 2, (cuuint64_t)W * a->Cin * 2, (cuuint64_t)H * W * a->Cin * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)p.Wt, (cuuint32_t)p.Ht, 1};
+    int s = make_map(&mah, a->a_hi, 4, dims, str, box);
+    if (s) return s;
+    s = make_map(&mal, a->a_lo, 4, dims, str, box);
+    if (s) return s;
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)a->Cout};
+    const cuuint64_t str[1] = {(cuuint64_t)Ktot * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)BN};
+    int s = make_map(&mbh, w_hi, 2, dims, str, box);
+    if (s) return s;
+    s = make_map(&mbl, w_lo, 2, dims, str, box);
+    if (s) return s;
+  }
+  cudaStream_t st = as_stream(stream);
+  if (BN == 256) return launch_tc<256>(mah, mal, mbh, mbl, p, st);
+  if (BN == 128) return launch_tc<128>(mah, mal, mbh, mbl, p, st);
+  return launch_tc<64>(mah, mal, mbh, mbl, p, st);
+}

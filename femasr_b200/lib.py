@@ -23,6 +23,9 @@ class FemasrError(RuntimeError):
     pass
 
 
+_I, _V, _Z, _D, _F = C.c_int, C.c_void_p, C.c_size_t, C.c_double, C.c_float
+
+
 class NetConfig(C.Structure):
     _fields_ = [("scale_factor", C.c_int), ("n_e", C.c_int), ("e_dim", C.c_int), ("in_channel", C.c_int),
                 ("use_quantize", C.c_int), ("use_residual", C.c_int), ("gemm_path", C.c_int)]
@@ -37,9 +40,15 @@ class IgemmArgs(C.Structure):
                 ("act", C.c_int)]
 
 
+class TcArgs(C.Structure):
+    _fields_ = [("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("w_blob", C.c_void_p), ("bias", C.c_void_p),
+                ("res1", C.c_void_p), ("res2", C.c_void_p), ("y", C.c_void_p),
+                ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
+                ("ksize", C.c_int), ("act", C.c_int)]
+
+
 # name -> (restype, argtypes); must list every symbol include/femasr_b200.h declares
 # (tests/test_abi.py checks the two against each other).
-_I, _V, _Z, _D, _F = C.c_int, C.c_void_p, C.c_size_t, C.c_double, C.c_float
 SIGNATURES = {
     "femasr_last_error": (C.c_char_p, []),
     "femasr_abi_version": (_I, []),
@@ -61,6 +70,10 @@ SIGNATURES = {
     "femasr_copy_window": (_I, [_V, _V] + [_I] * 12 + [_V]),
     "femasr_pack_weight": (_I, [_V, _V, _I, _I, _I, _I, _V]),
     "femasr_igemm_simt": (_I, [C.POINTER(IgemmArgs), _V]),
+    "femasr_tc_weight_bytes": (_Z, [_I, _I, _I, _I]),
+    "femasr_tc_pack_weight": (_I, [_V, _V, _I, _I, _I, _I, _V]),
+    "femasr_tc_prepare": (_I, [_V, _V, _V, _I, _V, _V, _V, _V, _I, _I, _I, _I, _I, _F, _V]),
+    "femasr_tc_igemm": (_I, [C.POINTER(TcArgs), _V]),
     "femasr_gn_scratch_floats": (_Z, [_I, _I, _I]),
     "femasr_gn_stats": (_I, [_V, _V, _V, _V, _V, _V, _I, _I, _I, _F, _V]),
     "femasr_ln_stats": (_I, [_V, _V, _V, _I, _I, _F, _V]),

@@ -138,6 +138,32 @@ typedef struct {
 } femasr_igemm_args;
 int femasr_igemm_simt(const femasr_igemm_args* a, void* stream);
 
+/* ---- tcgen05 tensor-core implicit GEMM (gemm_path 1): same contract as femasr_igemm_simt for ksize 1|3,
+ * stride 1, Cin%64==0, Cout%64==0, computed as a 3-product split-fp16 GEMM (a_hi*w_hi + a_hi*w_lo + a_lo*w_hi,
+ * fp32 accumulate in TMEM).  The activation operand is staged once per layer as two fp16 NHWC planes by
+ * femasr_tc_prepare (which also applies the GN+SiLU / LayerNorm prologue and the nearest x2 upsample);
+ * weights are packed once by femasr_tc_pack_weight into a blob of femasr_tc_weight_bytes bytes. */
+typedef struct {
+  const void* a_hi;        /* fp16 NHWC [B,H,W,Cin] at the conv-input resolution (after any upsample) */
+  const void* a_lo;
+  const void* w_blob;      /* from femasr_tc_pack_weight */
+  const float* bias;       /* [Cout] or NULL */
+  const float* res1;       /* fp32 NHWC like y, or NULL; may alias y */
+  const float* res2;
+  float* y;                /* fp32 NHWC [B,H,W,Cout] */
+  int B, H, W, Cin, Cout;
+  int ksize;               /* 1 or 3 (pad 1) */
+  int act;                 /* FEMASR_ACT_* */
+} femasr_tc_args;
+size_t femasr_tc_weight_bytes(int Cout, int Cin, int kh, int kw);
+int femasr_tc_pack_weight(const float* w_oihw, void* blob, int Cout, int Cin, int kh, int kw, void* stream);
+/* mode FEMASR_PRO_NONE | GN_SILU (pro_a/pro_b = scale/shift tables) | LN (gamma/beta, C=256, stats computed
+ * in-kernel).  x fp32 NHWC [B,H,W,C] -> a_hi/a_lo fp16 NHWC [B,H*u,W*u,C], u = upsample ? 2 : 1. */
+int femasr_tc_prepare(const float* x, void* a_hi, void* a_lo, int mode, const float* pro_a, const float* pro_b,
+                      const float* gamma, const float* beta, int B, int H, int W, int C, int upsample,
+                      float eps, void* stream);
+int femasr_tc_igemm(const femasr_tc_args* a, void* stream);
+
 /* GroupNorm(32 groups, eps) statistics of NHWC x[B,HW,C] folded with the affine parameters into
  * per-(sample,channel) scale/shift: scale = rstd*gamma, shift = beta - mean*rstd*gamma
  * (nn.GroupNorm, fema_utils.py:21-22).  `scratch` >= femasr_gn_scratch_floats(B,HW,C) floats. */

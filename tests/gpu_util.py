@@ -64,3 +64,33 @@ def ln_stats(x_tokens, eps=1e-5):
     rs = torch.empty(M, device=x_tokens.device)
     L.check(lib.femasr_ln_stats(p(x_tokens), p(mu), p(rs), M, Cc, eps, S()))
     return mu, rs
+
+
+def tc_pack(w_oihw):
+    lib = L.load()
+    co, ci, kh, kw = w_oihw.shape
+    blob = torch.empty(lib.femasr_tc_weight_bytes(co, ci, kh, kw), dtype=torch.uint8, device=w_oihw.device)
+    w = w_oihw.contiguous()
+    L.check(lib.femasr_tc_pack_weight(p(w), p(blob), co, ci, kh, kw, S()))
+    return blob
+
+
+def tc_prepare(x_nhwc, mode=0, pro_a=None, pro_b=None, gamma=None, beta=None, upsample=0, eps=1e-6):
+    lib = L.load()
+    B, H, W, Cc = x_nhwc.shape
+    u = 2 if upsample else 1
+    hi = torch.empty(B, H * u, W * u, Cc, dtype=torch.float16, device=x_nhwc.device)
+    lo = torch.empty_like(hi)
+    L.check(lib.femasr_tc_prepare(p(x_nhwc), p(hi), p(lo), mode, p(pro_a), p(pro_b), p(gamma), p(beta), B, H, W, Cc,
+                                  upsample, eps, S()))
+    return hi, lo
+
+
+def tc_igemm(hi, lo, blob, bias, Cout, ksize=3, act=0, res1=None, res2=None, y=None):
+    lib = L.load()
+    B, H, W, Cin = hi.shape
+    if y is None:
+        y = torch.empty(B, H, W, Cout, device=hi.device)
+    a = L.TcArgs(p(hi), p(lo), p(blob), p(bias), p(res1), p(res2), p(y), B, H, W, Cin, Cout, ksize, act)
+    L.check(lib.femasr_tc_igemm(C.byref(a), S()))
+    return y

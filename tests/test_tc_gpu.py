@@ -1,0 +1,145 @@
+"""GPU: the tcgen05 split-fp16 implicit GEMM (gemm_path 1) against fp64 ATen on CPU, through the C ABI,
+and the whole network on that path against the reference goldens / the oracle.
+
+Accuracy bar for the kernel: the 3-product split carries ~22 significand bits per operand, so errors must
+sit at fp32-GEMM level: <= 4e-6 * sqrt(K) * |a|rms*|w|rms-scaled bound below (checked against fp64 truth)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from femasr_b200 import lib as L
+from femasr_b200.spec import random_state_dict
+from oracle import femasr_oracle as O
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def rel_err(got, want64):
+    return ((got.double().cpu() - want64).abs().max() / want64.abs().max()).item()
+
+
+def test_split_planes(cuda):
+    x = rnd(2, 5, 7, 64, seed=1, scale=3.0)
+    x[0, 0, 0, :8] = torch.tensor([0.0, 1e-7, -3e-5, 70000.0, -70000.0, 1.0, 0.333333, 1e-3])
+    hi, lo = G.tc_prepare(x.to(cuda))
+    rec = hi.float().cpu() + lo.float().cpu()
+    xc = x.clamp(-65504, 65504)
+    err = (rec - xc).abs()
+    bound = torch.maximum(xc.abs() * 2.0 ** -21, torch.tensor(2.0 ** -24))
+    assert (err <= bound).all(), "hi+lo must reproduce x to ~22 bits (or the fp16 subnormal floor)"
+    # upsample replication
+    hi2, lo2 = G.tc_prepare(x.to(cuda), upsample=1)
+    want = hi.repeat_interleave(2, 1).repeat_interleave(2, 2)
+    assert torch.equal(hi2, want) and torch.equal(lo2, lo.repeat_interleave(2, 1).repeat_interleave(2, 2))
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [
+    (1, 16, 16, 64, 64), (2, 16, 24, 128, 128), (1, 24, 40, 256, 256), (2, 9, 72, 256, 128),
+    (1, 33, 17, 128, 64), (1, 8, 8, 512, 256), (3, 64, 64, 64, 64)])
+def test_tc_conv3x3(cuda, B, H, W, Cin, Cout):
+    x, w, b = rnd(B, Cin, H, W, seed=2), rnd(Cout, Cin, 3, 3, seed=3, scale=0.03), rnd(Cout, seed=4)
+    want = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    hi, lo = G.tc_prepare(G.nhwc(x).to(cuda))
+    y = G.tc_igemm(hi, lo, G.tc_pack(w.to(cuda)), b.to(cuda), Cout, 3)
+    e = rel_err(G.nchw(y), want)
+    f32 = rel_err(F.conv2d(x, w, b, padding=1), want)
+    print(f"tc conv {B}x{H}x{W} {Cin}->{Cout}: rel err {e:.2e} (ATen fp32: {f32:.2e})")
+    assert e <= max(4 * f32, 2e-6), f"tensor-core conv rel err {e:.3e} vs fp32 {f32:.3e}"
+
+
+@pytest.mark.parametrize("M,K,N,act", [(300, 256, 768, 0), (1000, 256, 1024, 1), (257, 1024, 256, 0), (4096, 256, 256, 0)])
+def test_tc_linear(cuda, M, K, N, act):
+    x, w, b = rnd(M, K, seed=5), rnd(N, K, seed=6, scale=0.05), rnd(N, seed=7)
+    res = rnd(M, N, seed=8)
+    want = F.linear(x.double(), w.double(), b.double())
+    if act:
+        want = F.gelu(want)
+    want = want + res.double()
+    hi, lo = G.tc_prepare(x.view(1, 1, M, K).to(cuda))
+    y = G.tc_igemm(hi, lo, G.tc_pack(w.view(N, K, 1, 1).to(cuda)), b.to(cuda), N, 1, act, res1=res.view(1, 1, M, N).to(cuda))
+    e = rel_err(y.view(M, N), want)
+    print(f"tc linear {M}x{K}x{N}: rel err {e:.2e}")
+    assert e <= 3e-6
+
+
+def test_tc_prologues(cuda):
+    B, H, W, Cc = 2, 16, 16, 128
+    x = rnd(B, Cc, H, W, seed=9, scale=2.0) + 0.5
+    gamma, beta = 1 + 0.2 * rnd(Cc, seed=10), 0.2 * rnd(Cc, seed=11)
+    want = F.silu(F.group_norm(x, 32, gamma, beta, 1e-6))
+    xg = G.nhwc(x).to(cuda)
+    sc, sh = G.gn_tables(xg, gamma.to(cuda), beta.to(cuda))
+    hi, lo = G.tc_prepare(xg, L.PRO_GN_SILU, sc, sh)
+    got = (hi.float() + lo.float()).permute(0, 3, 1, 2).cpu()
+    assert (got - want).abs().max().item() <= 5e-6
+    t = rnd(777, 256, seed=12, scale=2.0) + 0.3
+    g2, b2 = 1 + 0.2 * rnd(256, seed=13), 0.2 * rnd(256, seed=14)
+    want = F.layer_norm(t, (256,), g2, b2, 1e-5)
+    hi, lo = G.tc_prepare(t.view(1, 1, 777, 256).to(cuda), L.PRO_LN, gamma=g2.to(cuda), beta=b2.to(cuda), eps=1e-5)
+    got = (hi.float() + lo.float()).view(777, 256).cpu()
+    assert (got - want).abs().max().item() <= 5e-6
+
+
+def make_net(scale, e_dim, sd, cuda):
+    from basicsr.archs.femasr_arch import FeMaSRNet
+    net = FeMaSRNet(codebook_params=[[32, 1024, e_dim]], LQ_stage=True, scale_factor=scale, gemm_path=1)
+    net.load_state_dict(sd, strict=True)
+    return net.to(cuda).eval()
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_tensor_core_path(cuda, path):
+    g = np.load(path)
+    scale, e_dim, entry = int(g["scale"]), int(g["e_dim"]), str(g["entry"])
+    sd = random_state_dict(scale, e_dim, seed=int(g["seed"]), init=str(g["init"]))
+    net = make_net(scale, e_dim, sd, cuda)
+    x = torch.from_numpy(g["input"]).to(cuda)
+    with torch.no_grad():
+        if entry == "forward":
+            out, loss, sem, idx = net(x)
+            mism = int((idx[0].cpu().numpy() != g["indices"]).sum())
+            assert mism == 0, f"{mism}/{g['indices'].size} codebook index mismatches"
+            np.testing.assert_allclose(loss.item(), float(g["loss"]), rtol=2e-5)
+        elif entry == "test":
+            out = net.test(x)
+        elif entry == "test_tile":
+            out = net.test_tile(x, int(g["arg_tile_size"]), int(g["arg_tile_pad"]))
+        else:
+            out = net.decode_indices(x)
+    err = np.abs(out.cpu().numpy() - g["out"]).max()
+    print(f"{os.path.basename(path)}: tensor-core path output max-abs {err:.2e}")
+    assert err <= 1e-3, f"output max-abs {err:.3e}"
+
+
+def test_stage_taps_tensor_core_path(cuda):
+    scale, e_dim = 4, 256
+    sd = random_state_dict(scale, e_dim, seed=31, init="perturbed")
+    net = make_net(scale, e_dim, sd, cuda)
+    x = torch.rand((2, 3, 48, 32), generator=torch.Generator().manual_seed(32))
+    taps = {}
+    with torch.no_grad():
+        want, wloss, _, widx = O.encode_and_decode(sd, x, scale, taps)
+    eng = net._native(cuda)
+    names = ["swin", "up1", "up2", "z", "zq", "after_quant", "dec0", "dec1", "dec2"]
+    out, loss, idx, got = eng.forward(x.to(cuda), taps=names)
+    expect = {"swin": taps["enc0"], "up1": taps["enc1"], "up2": taps["enc2"], "z": taps["z"], "zq": taps["zq"],
+              "after_quant": taps["after_quant"], "dec0": taps["dec0"] + taps["enc1"],
+              "dec1": taps["dec1"] + taps["enc2"], "dec2": taps["dec2"]}
+    report = {n: (got[n].permute(0, 3, 1, 2).cpu() - expect[n]).abs().max().item() / expect[n].abs().max().item()
+              for n in names}
+    print("tensor-core path relative stage errors:", {k: f"{v:.2e}" for k, v in report.items()})
+    assert torch.equal(idx.cpu(), widx[0]), "indices not bit-exact"
+    for n, v in report.items():
+        assert v <= 2e-4, f"stage {n}: relative max error {v:.3e}"
+    assert (out.cpu() - want).abs().max().item() <= 1e-3
