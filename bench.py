@@ -98,22 +98,33 @@ class ClockSampler:
 
 
 def cpu_arm(args, steps: int, warmup: int, budget_s: float = 25.0):
-    """Times the CPU oracle port (ATen-CPU fp32, all host threads) on a bounded sample of the workload:
-    `sample_b` images of the same 128x128 x4 config per step.  Returns (img/s, dict)."""
+    """Times the CPU oracle port (ATen-CPU fp32) on a bounded sample of the workload: `sample_b` images of the
+    same 128x128 x4 config per step.  The thread count is calibrated (all cores is often slower than fewer on a
+    many-core host) and the best one is used and reported as `cores`.  Returns (img/s, ms/step, sample_b, info)."""
     import torch
     from femasr_b200.spec import random_state_dict
     from oracle import femasr_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    ncpu = os.cpu_count() or 1
     sd = random_state_dict(args.scale, args.e_dim, seed=0, init="default")
     g = torch.Generator().manual_seed(1)
+    t_begin = time.perf_counter()
     with torch.no_grad():
-        x1 = torch.rand(1, 3, args.lr, args.lr, generator=g)
-        t0 = time.perf_counter()
-        O.encode_and_decode(sd, x1, args.scale)
-        t1 = time.perf_counter() - t0                      # also the warm-up
-        per_step_budget = budget_s / max(1, steps + warmup)
-        sample_b = int(max(1, min(args.batch, per_step_budget / max(t1, 1e-3))))
+        O.encode_and_decode(sd, torch.rand(1, 3, 32, 32, generator=g), args.scale)     # warm thread pools / primitives
+        xc = torch.rand(2, 3, args.lr, args.lr, generator=g)
+        best_t, best_n = None, ncpu
+        for n in sorted({ncpu, max(1, ncpu // 2), min(ncpu, 32), min(ncpu, 16)}, reverse=True):
+            torch.set_num_threads(n)
+            t0 = time.perf_counter()
+            O.encode_and_decode(sd, xc, args.scale)
+            dt = (time.perf_counter() - t0) / 2
+            if best_t is None or dt < best_t:
+                best_t, best_n = dt, n
+            if time.perf_counter() - t_begin > budget_s * 0.5:
+                break
+        torch.set_num_threads(best_n)
+        left = max(2.0, budget_s - (time.perf_counter() - t_begin))
+        per_step_budget = left / max(1, steps + warmup)
+        sample_b = int(max(1, min(args.batch, per_step_budget / max(best_t, 1e-3))))
         x = torch.rand(sample_b, 3, args.lr, args.lr, generator=g)
         for _ in range(warmup):
             O.encode_and_decode(sd, x, args.scale)
@@ -124,9 +135,10 @@ def cpu_arm(args, steps: int, warmup: int, budget_s: float = 25.0):
             times.append(time.perf_counter() - t0)
     total = sum(times)
     ips = sample_b * steps / total
-    info = {"value": round(ips, 4), "unit": "images/s", "cores": cores, "kind": "port",
+    info = {"value": round(ips, 4), "unit": "images/s", "cores": best_n, "host_cpus": ncpu, "kind": "port",
             "sample": f"{steps} steps x {sample_b} of the {args.batch} images of one batch ({args.lr}x{args.lr} LR, x{args.scale}, "
-                      f"e{args.e_dim}), oracle/femasr_oracle.py on torch-CPU fp32, {cores} threads"}
+                      f"e{args.e_dim}), oracle/femasr_oracle.py (the reference's ATen-CPU arithmetic) fp32, "
+                      f"{best_n} threads (best of a calibration over thread counts on {ncpu} CPUs)"}
     return ips, total / steps * 1e3, sample_b, info
 
 

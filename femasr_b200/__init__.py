@@ -12,5 +12,6 @@ __version__ = "0.1.0"
 
 
 def default_gemm_path() -> int:
-    """0 = fp32 SIMT implicit GEMM, 1 = tcgen05 split-fp16 tensor-core GEMM (FEMASR_GEMM_PATH overrides)."""
-    return int(os.environ.get("FEMASR_GEMM_PATH", "0"))
+    """1 = tcgen05 split-fp16 tensor-core GEMM (default), 0 = fp32 SIMT implicit GEMM (exact-arithmetic
+    debug path); FEMASR_GEMM_PATH overrides."""
+    return int(os.environ.get("FEMASR_GEMM_PATH", "1"))

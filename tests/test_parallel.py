@@ -1,0 +1,54 @@
+"""CPU, world_size 2 over gloo: batch sharding + the single all-gather of outputs (host logic of the
+multi-GPU path; the per-rank forward is a stub here because the product path needs a GPU)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from femasr_b200.parallel import all_gather_outputs, shard_counts, shard_range, sharded_forward
+
+
+def test_shard_ranges_partition_the_batch():
+    for n in (0, 1, 2, 7, 32, 255, 256):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = shard_counts(n, world)
+            assert sum(sizes) == n and max(sizes) - min(sizes) <= 1
+
+
+def _stub_sr(x):                       # stands in for FeMaSRNet.test: x4 nearest "SR" with a per-image tag
+    return x.repeat_interleave(4, 2).repeat_interleave(4, 3) * 2.0 + 1.0
+
+
+def _worker(rank, world, port, n, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        x = torch.rand(n, 3, 8, 8, generator=g)
+        out = sharded_forward(_stub_sr, x, rank, world, out_shape_fn=lambda s: (s[0], 3, s[2] * 4, s[3] * 4))
+        ok = torch.equal(out, _stub_sr(x))
+        # equal shards take the all_gather_into_tensor fast path
+        a, b = shard_range(n, rank, world)
+        out2 = all_gather_outputs(_stub_sr(x[a:b]), shard_counts(n, world)) if n % world == 0 else out
+        ok = ok and torch.equal(out2, _stub_sr(x))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [8, 5, 1])
+def test_world2_gloo_gather(n):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, n, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
