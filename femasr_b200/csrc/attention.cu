@@ -2,6 +2,8 @@
 // One CTA per (window, head); one thread per query token.  The cyclic shift (torch.roll), the window
 // partition/reverse permutes and the 0/-100 shift mask of network_swinir.py:216-279 are pure index
 // arithmetic here; nothing is materialised.  0.9% of the path's FLOPs.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace femasr {
@@ -80,6 +82,190 @@ __global__ void __launch_bounds__(64) window_attention_kernel(const float* __res
     reinterpret_cast<float4*>(orow)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core variant (warp-level mma.sync m16n8k16, fp16 operands split hi/lo, fp32 accumulate): the
+// 64x32x64 per-(window, head) products are far too small for a tcgen05 tile, so the legacy warp MMA path is
+// the right tool here.  One CTA of 4 warps per (window, head); warp w owns query rows [16w, 16w+16).
+//   S = (q*scale) K^T  -> + rel-pos bias (+ shift mask) -> softmax (fp32, in registers) -> O = P V.
+// Both products use the same 3-term split as the big GEMMs (lo*hi + hi*lo + hi*hi).
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half hx = __float2half_rn(x), hy = __float2half_rn(y);
+  const __half lx = __float2half_rn(x - __half2float(hx)), ly = __float2half_rn(y - __half2float(hy));
+  hi = (uint32_t)__half_as_ushort(hx) | ((uint32_t)__half_as_ushort(hy) << 16);
+  lo = (uint32_t)__half_as_ushort(lx) | ((uint32_t)__half_as_ushort(ly) << 16);
+}
+
+constexpr int KS_LD = 40;   // K[key][dim] row stride in halves (pad 32 -> 40: conflict-free fragment loads)
+constexpr int VT_LD = 72;   // V^T[dim][key] row stride in halves (pad 64 -> 72)
+
+__global__ void __launch_bounds__(128) window_attention_mma_kernel(const float* __restrict__ qkv,
+                                                                   const float* __restrict__ bias_full,
+                                                                   float* __restrict__ out, __half* __restrict__ out_hi,
+                                                                   __half* __restrict__ out_lo, int H, int W, int C,
+                                                                   int heads, int shift) {
+  __shared__ __align__(16) __half Kh[WT * KS_LD], Kl[WT * KS_LD];
+  __shared__ __align__(16) __half Vth[HD * VT_LD], Vtl[HD * VT_LD];
+  __shared__ int region[WT];
+  __shared__ long toks[WT];
+  const int head = blockIdx.x % heads;
+  const int win = blockIdx.x / heads;
+  const int nwx = W / WS, nwy = H / WS;
+  const int b = win / (nwx * nwy);
+  const int wrem = win - b * nwx * nwy;
+  const int wy = wrem / nwx, wx = wrem - wy * nwx;
+  const int tid = threadIdx.x;
+  {
+    // staging: thread t handles token t/2, dims [16*(t&1), +16) of K and V
+    const int j = tid >> 1, half = tid & 1;
+    const int ys = wy * WS + j / WS, xs = wx * WS + (j % WS);
+    const int yo = (ys + shift) % H, xo = (xs + shift) % W;
+    const long tok = ((long)b * H + yo) * W + xo;
+    if (half == 0) {
+      toks[j] = tok;
+      region[j] = shift > 0 ? shift_region(ys, H, shift) * 3 + shift_region(xs, W, shift) : 0;
+    }
+    const float4* kp = reinterpret_cast<const float4*>(qkv + tok * (3 * C) + C + head * HD + half * 16);
+    const float4* vp = reinterpret_cast<const float4*>(qkv + tok * (3 * C) + 2 * C + head * HD + half * 16);
+    __align__(16) __half kh[16], kl[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 kv = __ldg(kp + i);
+      const float kk[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __half h = __float2half_rn(kk[e]);
+        kh[4 * i + e] = h;
+        kl[4 * i + e] = __float2half_rn(kk[e] - __half2float(h));
+      }
+      const float4 vv = __ldg(vp + i);
+      const float ve[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int d = half * 16 + 4 * i + e;
+        const __half h = __float2half_rn(ve[e]);
+        Vth[d * VT_LD + j] = h;
+        Vtl[d * VT_LD + j] = __float2half_rn(ve[e] - __half2float(h));
+      }
+    }
+    uint4* dh = reinterpret_cast<uint4*>(&Kh[j * KS_LD + half * 16]);
+    uint4* dl = reinterpret_cast<uint4*>(&Kl[j * KS_LD + half * 16]);
+    dh[0] = reinterpret_cast<const uint4*>(kh)[0]; dh[1] = reinterpret_cast<const uint4*>(kh)[1];
+    dl[0] = reinterpret_cast<const uint4*>(kl)[0]; dl[1] = reinterpret_cast<const uint4*>(kl)[1];
+  }
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+  const int r0 = warp * 16 + g, r1 = r0 + 8;
+  const float scale = 0.17677669529663687f;
+  // Q fragments (A operand), scaled then split
+  uint32_t qh[2][4], ql[2][4];
+  {
+    const float* q0 = qkv + toks[r0] * (3 * C) + head * HD;
+    const float* q1 = qkv + toks[r1] * (3 * C) + head * HD;
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt) {
+      const float2 a = __ldg(reinterpret_cast<const float2*>(q0 + 16 * kt + 2 * c));
+      const float2 bq = __ldg(reinterpret_cast<const float2*>(q1 + 16 * kt + 2 * c));
+      const float2 cq = __ldg(reinterpret_cast<const float2*>(q0 + 16 * kt + 8 + 2 * c));
+      const float2 dq = __ldg(reinterpret_cast<const float2*>(q1 + 16 * kt + 8 + 2 * c));
+      split2(a.x * scale, a.y * scale, qh[kt][0], ql[kt][0]);
+      split2(bq.x * scale, bq.y * scale, qh[kt][1], ql[kt][1]);
+      split2(cq.x * scale, cq.y * scale, qh[kt][2], ql[kt][2]);
+      split2(dq.x * scale, dq.y * scale, qh[kt][3], ql[kt][3]);
+    }
+  }
+  float s[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt) {
+      const int off = (8 * nt + g) * KS_LD + 16 * kt + 2 * c;
+      const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&Kh[off]), bh1 = *reinterpret_cast<const uint32_t*>(&Kh[off + 8]);
+      const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&Kl[off]), bl1 = *reinterpret_cast<const uint32_t*>(&Kl[off + 8]);
+      mma16816(s[nt], ql[kt], bh0, bh1);
+      mma16816(s[nt], qh[kt], bl0, bl1);
+      mma16816(s[nt], qh[kt], bh0, bh1);
+    }
+  }
+  // bias, mask, softmax numerator (rows r0 and r1; each row is spread over the 4 lanes of a quad)
+  const float* b0p = bias_full + ((long)head * WT + r0) * WT;
+  const float* b1p = bias_full + ((long)head * WT + r1) * WT;
+  const int reg0 = region[r0], reg1 = region[r1];
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int col = 8 * nt + 2 * c;
+    const float2 bb0 = __ldg(reinterpret_cast<const float2*>(b0p + col));
+    const float2 bb1 = __ldg(reinterpret_cast<const float2*>(b1p + col));
+    s[nt][0] += bb0.x; s[nt][1] += bb0.y; s[nt][2] += bb1.x; s[nt][3] += bb1.y;
+    if (shift > 0) {
+      const int rc0 = region[col], rc1 = region[col + 1];
+      if (rc0 != reg0) s[nt][0] += -100.0f;
+      if (rc1 != reg0) s[nt][1] += -100.0f;
+      if (rc0 != reg1) s[nt][2] += -100.0f;
+      if (rc1 != reg1) s[nt][3] += -100.0f;
+    }
+    m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+    m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    s[nt][0] = __expf(s[nt][0] - m0); s[nt][1] = __expf(s[nt][1] - m0);
+    s[nt][2] = __expf(s[nt][2] - m1); s[nt][3] = __expf(s[nt][3] - m1);
+    sum0 += s[nt][0] + s[nt][1];
+    sum1 += s[nt][2] + s[nt][3];
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  // O = P V  (P unnormalised in [0,1]; rows scaled by 1/sum at the end)
+  float o[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+    uint32_t ph[4], pl[4];
+    split2(s[2 * kt][0], s[2 * kt][1], ph[0], pl[0]);
+    split2(s[2 * kt][2], s[2 * kt][3], ph[1], pl[1]);
+    split2(s[2 * kt + 1][0], s[2 * kt + 1][1], ph[2], pl[2]);
+    split2(s[2 * kt + 1][2], s[2 * kt + 1][3], ph[3], pl[3]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int off = (8 * nt + g) * VT_LD + 16 * kt + 2 * c;
+      const uint32_t vh0 = *reinterpret_cast<const uint32_t*>(&Vth[off]), vh1 = *reinterpret_cast<const uint32_t*>(&Vth[off + 8]);
+      const uint32_t vl0 = *reinterpret_cast<const uint32_t*>(&Vtl[off]), vl1 = *reinterpret_cast<const uint32_t*>(&Vtl[off + 8]);
+      mma16816(o[nt], pl, vh0, vh1);
+      mma16816(o[nt], ph, vl0, vl1);
+      mma16816(o[nt], ph, vh0, vh1);
+    }
+  }
+  const float i0 = 1.0f / sum0, i1 = 1.0f / sum1;
+  const long e0 = toks[r0] * C + head * HD, e1 = toks[r1] * C + head * HD;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int col = 8 * nt + 2 * c;
+    if (out_hi) {            // split fp16 planes: directly the proj GEMM's A operand
+      uint32_t h, l;
+      split2(o[nt][0] * i0, o[nt][1] * i0, h, l);
+      *reinterpret_cast<uint32_t*>(out_hi + e0 + col) = h; *reinterpret_cast<uint32_t*>(out_lo + e0 + col) = l;
+      split2(o[nt][2] * i1, o[nt][3] * i1, h, l);
+      *reinterpret_cast<uint32_t*>(out_hi + e1 + col) = h; *reinterpret_cast<uint32_t*>(out_lo + e1 + col) = l;
+    } else {
+      *reinterpret_cast<float2*>(out + e0 + col) = make_float2(o[nt][0] * i0, o[nt][1] * i0);
+      *reinterpret_cast<float2*>(out + e1 + col) = make_float2(o[nt][2] * i1, o[nt][3] * i1);
+    }
+  }
+}
+
 // bias_full[h][i][j] = table[rel_index(i,j)][h],  rel_index = (yi-yj+7)*15 + (xi-xj+7)   (network_swinir.py:91-101,127-129)
 __global__ void expand_rel_bias_kernel(const float* __restrict__ table, float* __restrict__ bias_full, int heads) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,6 +291,20 @@ extern "C" int femasr_window_attention(const float* qkv, const float* bias_full,
   const long blocks = (long)B * (H / WS) * (W / WS) * heads;
   window_attention_kernel<<<(unsigned)blocks, 64, 0, as_stream(stream)>>>(qkv, bias_full, out, H, W, C, heads, shift);
   return launch_status("window_attention_kernel");
+}
+
+extern "C" int femasr_window_attention_mma(const float* qkv, const float* bias_full, float* out, void* out_hi,
+                                           void* out_lo, int B, int H, int W, int C, int heads, int shift, void* stream) {
+  FEMASR_CHECK_ARG(qkv && bias_full && (out || (out_hi && out_lo)), "window_attention_mma: null pointer");
+  FEMASR_CHECK_ARG(!out_hi == !out_lo, "window_attention_mma: out_hi and out_lo go together");
+  FEMASR_CHECK_ARG(B > 0 && H > 0 && W > 0, "window_attention_mma: empty input");
+  FEMASR_CHECK_ARG(H % WS == 0 && W % WS == 0, "window_attention_mma: H and W must be multiples of the 8x8 window");
+  FEMASR_CHECK_ARG(heads > 0 && C == heads * HD, "window_attention_mma: C must equal heads*32");
+  FEMASR_CHECK_ARG(shift == 0 || shift == WS / 2, "window_attention_mma: shift must be 0 or 4");
+  const long blocks = (long)B * (H / WS) * (W / WS) * heads;
+  window_attention_mma_kernel<<<(unsigned)blocks, 128, 0, as_stream(stream)>>>(
+      qkv, bias_full, out, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), H, W, C, heads, shift);
+  return launch_status("window_attention_mma_kernel");
 }
 
 extern "C" int femasr_expand_rel_bias(const float* table, float* bias_full, int heads, void* stream) {

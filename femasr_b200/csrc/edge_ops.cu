@@ -38,31 +38,43 @@ __global__ void __launch_bounds__(256) in_conv_kernel(const float* __restrict__ 
   reinterpret_cast<float4*>(y + pix * Cout)[q] = acc;
 }
 
-// one thread per output pixel; weights [9*Cin][3] in shared memory (broadcast reads)
-template <int CIN>
-__global__ void __launch_bounds__(128) out_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                       const float* __restrict__ bias, float* __restrict__ y,
-                                                       int B, int H, int W) {
-  __shared__ __align__(16) float ws[9 * CIN * 3 + 4];
-  for (int i = threadIdx.x; i < 9 * CIN * 3; i += 128) ws[i] = w[i];
+// out_conv: 3x3, Cin=64 -> 3.  The input tile (with halo) is staged in shared memory by coalesced 16-byte
+// loads (NHWC rows are contiguous), pixel stride padded to 68 floats so the per-thread float4 reads are
+// bank-conflict free; the 1728 weights sit in __constant__ memory (uniform across the warp -> FFMA with a
+// constant operand, no load instruction).  One thread per output pixel, tile = 4 rows x 32 cols.
+constexpr int OC_CIN = 64, OC_TH = 4, OC_TW = 32, OC_PS = 68;   // pixel stride in floats
+__constant__ float c_outconv_w[9 * OC_CIN * 3];
+__constant__ float c_outconv_b[4];
+
+__global__ void __launch_bounds__(OC_TH * OC_TW) out_conv_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                 int B, int H, int W) {
+  extern __shared__ __align__(16) float tile[];      // [(OC_TH+2)][(OC_TW+2)][OC_PS]
+  const int x0 = blockIdx.x * OC_TW, y0 = blockIdx.y * OC_TH, b = blockIdx.z;
+  constexpr int TWH = OC_TW + 2, THH = OC_TH + 2;
+  // cooperative halo load: (THH*TWH) pixels x 16 float4
+  for (int i = threadIdx.x; i < THH * TWH * (OC_CIN / 4); i += OC_TH * OC_TW) {
+    const int c4 = i % (OC_CIN / 4);
+    const int pp = i / (OC_CIN / 4);
+    const int px = pp % TWH, py = pp / TWH;
+    const int gy = y0 + py - 1, gx = x0 + px - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+      v = __ldg(reinterpret_cast<const float4*>(x + (((long)b * H + gy) * W + gx) * OC_CIN) + c4);
+    *reinterpret_cast<float4*>(&tile[(py * TWH + px) * OC_PS + c4 * 4]) = v;
+  }
   __syncthreads();
-  const int ox = blockIdx.x * 128 + threadIdx.x;
-  const int oy = blockIdx.y, b = blockIdx.z;
-  if (ox >= W) return;
-  float a0 = bias[0], a1 = bias[1], a2 = bias[2];
-#pragma unroll
-  for (int kh = 0; kh < 3; ++kh) {
-    const int iy = oy + kh - 1;
-    if (iy < 0 || iy >= H) continue;
+  const int lx = threadIdx.x % OC_TW, ly = threadIdx.x / OC_TW;
+  const int ox = x0 + lx, oy = y0 + ly;
+  float a0 = c_outconv_b[0], a1 = c_outconv_b[1], a2 = c_outconv_b[2];
+#pragma unroll 1
+  for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
     for (int kw = 0; kw < 3; ++kw) {
-      const int ix = ox + kw - 1;
-      if (ix < 0 || ix >= W) continue;
-      const float4* px = reinterpret_cast<const float4*>(x + (((long)b * H + iy) * W + ix) * CIN);
-      const float* wt = ws + (kh * 3 + kw) * CIN * 3;
+      const float* px = &tile[((ly + kh) * TWH + lx + kw) * OC_PS];
+      const float* wt = c_outconv_w + (kh * 3 + kw) * OC_CIN * 3;
 #pragma unroll 4
-      for (int c4 = 0; c4 < CIN / 4; ++c4) {
-        const float4 v = __ldg(px + c4);
+      for (int c4 = 0; c4 < OC_CIN / 4; ++c4) {
+        const float4 v = *reinterpret_cast<const float4*>(px + c4 * 4);
         const float* wk = wt + c4 * 12;
         a0 = fmaf(v.x, wk[0], a0); a1 = fmaf(v.x, wk[1], a1); a2 = fmaf(v.x, wk[2], a2);
         a0 = fmaf(v.y, wk[3], a0); a1 = fmaf(v.y, wk[4], a1); a2 = fmaf(v.y, wk[5], a2);
@@ -70,10 +82,11 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const float* __restrict__
         a0 = fmaf(v.w, wk[9], a0); a1 = fmaf(v.w, wk[10], a1); a2 = fmaf(v.w, wk[11], a2);
       }
     }
+  if (ox < W && oy < H) {
+    const long plane = (long)H * W;
+    float* o = y + (long)b * 3 * plane + (long)oy * W + ox;
+    o[0] = a0; o[plane] = a1; o[2 * plane] = a2;
   }
-  const long plane = (long)H * W;
-  float* o = y + (long)b * 3 * plane + (long)oy * W + ox;
-  o[0] = a0; o[plane] = a1; o[2 * plane] = a2;
 }
 
 __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int KH, int KW) {
@@ -145,10 +158,20 @@ extern "C" int femasr_out_conv3x3(const float* x, const float* w, const float* b
                                   int Cin, void* stream) {
   FEMASR_CHECK_ARG(x && w && bias && y, "out_conv: null pointer");
   FEMASR_CHECK_ARG(B > 0 && H > 0 && W > 0, "out_conv: empty input");
-  FEMASR_CHECK_ARG(Cin == 64, "out_conv: Cin must be 64 (channel_query_dict[256])");
-  FEMASR_CHECK_ARG(H <= 65535 && B <= 65535, "out_conv: grid too large");
-  dim3 grid((unsigned)cdiv(W, 128), H, B);
-  out_conv_kernel<64><<<grid, 128, 0, as_stream(stream)>>>(x, w, bias, y, B, H, W);
+  FEMASR_CHECK_ARG(Cin == OC_CIN, "out_conv: Cin must be 64 (channel_query_dict[256])");
+  FEMASR_CHECK_ARG(cdiv(H, OC_TH) <= 65535 && B <= 65535, "out_conv: grid too large");
+  cudaStream_t st = as_stream(stream);
+  // weights travel through __constant__ memory; refreshed per call (stream-ordered) so several engines can coexist
+  FEMASR_CUDA(cudaMemcpyToSymbolAsync(c_outconv_w, w, sizeof(float) * 9 * OC_CIN * 3, 0, cudaMemcpyDeviceToDevice, st));
+  FEMASR_CUDA(cudaMemcpyToSymbolAsync(c_outconv_b, bias, sizeof(float) * 3, 0, cudaMemcpyDeviceToDevice, st));
+  constexpr int smem = (OC_TH + 2) * (OC_TW + 2) * OC_PS * (int)sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FEMASR_CUDA(cudaFuncSetAttribute(out_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)cdiv(W, OC_TW), (unsigned)cdiv(H, OC_TH), B);
+  out_conv_kernel<<<grid, OC_TH * OC_TW, smem, st>>>(x, y, B, H, W);
   return launch_status("out_conv_kernel");
 }
 

@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace femasr {
@@ -91,6 +93,7 @@ struct femasr_net {
   std::map<std::string, DevBuf> raw;      // fp32 copy in the reference layout
   std::map<std::string, DevBuf> packed;   // K-major GEMM operand / expanded rel bias / codebook^T
   std::map<std::string, DevBuf> tcw;      // tensor-core operand (split fp16), gemm_path 1
+  std::map<std::string, DevBuf> tcw_up;   // sub-pixel phase filters of the upsample-fused 3x3 convs
   DevBuf esq;
   std::map<std::string, Tap> taps;
   int last_launches = 0;
@@ -102,6 +105,7 @@ struct femasr_net {
     for (auto& kv : raw) cudaFree(kv.second.p);
     for (auto& kv : packed) cudaFree(kv.second.p);
     for (auto& kv : tcw) cudaFree(kv.second.p);
+    for (auto& kv : tcw_up) cudaFree(kv.second.p);
     cudaFree(esq.p);
   }
 };
@@ -223,7 +227,7 @@ struct Ctx {
   void conv(const std::string& wname, const float* x, float* y, int B, int Hin, int Win, int Cin, int Cout, int ksize,
             int stride, int upsample, int prologue, const float* pa, const float* pb, const float* gamma,
             const float* beta, int act, const float* res1, const float* res2, bool has_bias = true) {
-    if (has_bias && tc_eligible(wname, Cin, Cout, ksize, stride)) {
+    if (has_bias && tc_eligible(wname, Cin, Cout, ksize, stride, upsample)) {
       conv_tc(wname, x, y, B, Hin, Win, Cin, Cout, ksize, upsample, prologue, pa, pb, gamma, beta, act, res1, res2);
       return;
     }
@@ -243,34 +247,45 @@ struct Ctx {
     run("igemm_simt", flops, [&] { return femasr_igemm_simt(&a, st); });
   }
 
-  bool tc_eligible(const std::string& wname, int Cin, int Cout, int ksize, int stride) const {
-    return net->cfg.gemm_path == 1 && stride == 1 && (ksize == 1 || ksize == 3) && Cin % 64 == 0 && Cout % 64 == 0 &&
-           (dry() || net->tcw.count(wname + ".weight") != 0);
+  bool tc_eligible(const std::string& wname, int Cin, int Cout, int ksize, int stride, int upsample) const {
+    if (net->cfg.gemm_path != 1 || stride != 1 || (ksize != 1 && ksize != 3) || Cin % 64 || Cout % 64) return false;
+    if (dry()) return true;
+    return upsample ? net->tcw_up.count(wname + ".weight") != 0 : net->tcw.count(wname + ".weight") != 0;
   }
 
-  // tensor-core variant of conv(): stage the activation operand (prologue + upsample + fp16 split), then the
-  // tcgen05 implicit GEMM.  Allocation happens in dry runs too so the workspace size is exact.
+  // tensor-core variant of conv(): stage the activation operand (prologue + fp16 split) unless the producer
+  // already wrote split planes (pre_hi/pre_lo), then the tcgen05 implicit GEMM; optionally the result is
+  // emitted as split planes for the next GEMM (out_hi/out_lo) instead of fp32 y.  A fused nearest-x2 upsample
+  // runs as four sub-pixel 2x2 convs on the low-res operand.  Allocation happens in dry runs too.
   void conv_tc(const std::string& wname, const float* x, float* y, int B, int Hin, int Win, int Cin, int Cout, int ksize,
                int upsample, int prologue, const float* pa, const float* pb, const float* gamma, const float* beta,
-               int act, const float* res1, const float* res2) {
-    const int Hc = upsample ? 2 * Hin : Hin, Wc = upsample ? 2 * Win : Win;
-    const size_t plane_halves = (size_t)B * Hc * Wc * Cin;
-    float* ahi = ar.alloc((plane_halves + 1) / 2);
-    float* alo = ar.alloc((plane_halves + 1) / 2);
+               int act, const float* res1, const float* res2, const void* pre_hi = nullptr, const void* pre_lo = nullptr,
+               void* out_hi = nullptr, void* out_lo = nullptr) {
+    const size_t plane_halves = (size_t)B * Hin * Win * Cin;
+    float *ahi = nullptr, *alo = nullptr;
+    if (!pre_hi) {
+      ahi = ar.alloc((plane_halves + 1) / 2);
+      alo = ar.alloc((plane_halves + 1) / 2);
+    }
     if (!dry() && ok()) {
-      run("tc_prepare", 0.0, [&] {
-        return femasr_tc_prepare(x, ahi, alo, prologue, pa, pb, gamma, beta, B, Hin, Win, Cin, upsample,
-                                 prologue == FEMASR_PRO_LN ? 1e-5f : 1e-6f, st);
-      });
+      if (!pre_hi)
+        run("tc_prepare", 0.0, [&] {
+          return femasr_tc_prepare(x, ahi, alo, prologue, pa, pb, gamma, beta, B, Hin, Win, Cin, 0,
+                                   prologue == FEMASR_PRO_LN ? 1e-5f : 1e-6f, st);
+        });
       femasr_tc_args t;
       memset(&t, 0, sizeof(t));
-      t.a_hi = ahi; t.a_lo = alo; t.w_blob = net->tcw[wname + ".weight"].p; t.bias = P(wname + ".bias");
-      t.res1 = res1; t.res2 = res2; t.y = y; t.B = B; t.H = Hc; t.W = Wc; t.Cin = Cin; t.Cout = Cout;
-      t.ksize = ksize; t.act = act;
-      const double flops = 2.0 * B * Hc * Wc * (double)Cout * Cin * ksize * ksize;
+      t.a_hi = pre_hi ? pre_hi : ahi; t.a_lo = pre_hi ? pre_lo : alo;
+      t.w_blob = upsample ? net->tcw_up[wname + ".weight"].p : net->tcw[wname + ".weight"].p;
+      t.bias = P(wname + ".bias");
+      t.res1 = res1; t.res2 = res2; t.y = y; t.out_hi = out_hi; t.out_lo = out_lo;
+      t.B = B; t.H = Hin; t.W = Win; t.Cin = Cin; t.Cout = Cout; t.ksize = ksize; t.act = act; t.upsample = upsample;
+      const int u = upsample ? 2 : 1;
+      const double flops = 2.0 * B * (Hin * u) * (double)(Win * u) * Cout * Cin * ksize * ksize;   // algorithmic (reference) count
       run("tc_igemm", flops, [&] { return femasr_tc_igemm(&t, st); });
     }
-    ar.release(alo); ar.release(ahi);
+    if (alo) ar.release(alo);
+    if (ahi) ar.release(ahi);
   }
 
   // GroupNorm statistics of x folded into scale/shift tables (allocated by the caller)
@@ -314,22 +329,39 @@ struct Ctx {
     float* hid = ar.alloc(M * 4 * C);
     float* mu = ar.alloc(M);
     float* rs = ar.alloc(M);
-    const bool tc = net->cfg.gemm_path == 1;   // the tensor-core operand staging computes LayerNorm itself
+    const bool tc = net->cfg.gemm_path == 1 && (dry() || net->tcw.count(p + ".swin_blks.0.conv.weight") != 0);
     for (int r = 0; r < 4; ++r) {
       const std::string rp = p + ".swin_blks." + std::to_string(r);
       for (int b = 0; b < 6; ++b) {
         const std::string bp = rp + ".residual_group.blocks." + std::to_string(b);
         const float* in = b == 0 ? X : T;
-        if (!tc) run("ln_stats", 0.0, [&] { return femasr_ln_stats(in, mu, rs, (int)M, C, 1e-5f, st); });
+        const float* rb = P(bp + ".attn.relative_position_bias_table");
+        const double attn_flops = 2.0 * 2.0 * 64 * C * (double)M;
+        if (tc) {
+          // operands travel between the kernels as split fp16 planes: `ao` and `hid` are reinterpreted as
+          // [hi plane | lo plane] (same byte size as the fp32 tensors they replace)
+          __half* ao_hi = reinterpret_cast<__half*>(ao);  __half* ao_lo = ao_hi + M * C;
+          __half* hd_hi = reinterpret_cast<__half*>(hid); __half* hd_lo = hd_hi + M * 4 * C;
+          conv_tc(bp + ".attn.qkv", in, qkv, B, H, W, C, 3 * C, 1, 0, FEMASR_PRO_LN, nullptr, nullptr, P(bp + ".norm1.weight"),
+                  P(bp + ".norm1.bias"), 0, nullptr, nullptr);
+          run("window_attention_mma", attn_flops, [&] {
+            return femasr_window_attention_mma(qkv, rb, nullptr, ao_hi, ao_lo, B, H, W, C, 8, (b & 1) ? 4 : 0, st);
+          });
+          conv_tc(bp + ".attn.proj", nullptr, T, B, H, W, C, C, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0,
+                  in, nullptr, ao_hi, ao_lo);
+          conv_tc(bp + ".mlp.fc1", T, nullptr, B, H, W, C, 4 * C, 1, 0, FEMASR_PRO_LN, nullptr, nullptr, P(bp + ".norm2.weight"),
+                  P(bp + ".norm2.bias"), FEMASR_ACT_GELU, nullptr, nullptr, nullptr, nullptr, hd_hi, hd_lo);
+          conv_tc(bp + ".mlp.fc2", nullptr, T, B, H, W, 4 * C, C, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0,
+                  T, nullptr, hd_hi, hd_lo);
+          continue;
+        }
+        run("ln_stats", 0.0, [&] { return femasr_ln_stats(in, mu, rs, (int)M, C, 1e-5f, st); });
         conv(bp + ".attn.qkv", in, qkv, B, H, W, C, 3 * C, 1, 1, 0, FEMASR_PRO_LN, mu, rs, P(bp + ".norm1.weight"),
              P(bp + ".norm1.bias"), 0, nullptr, nullptr);
-        {
-          const float* rb = P(bp + ".attn.relative_position_bias_table");
-          run("window_attention", 2.0 * 2.0 * 64 * C * (double)M,
-              [&] { return femasr_window_attention(qkv, rb, ao, B, H, W, C, 8, (b & 1) ? 4 : 0, st); });
-        }
+        run("window_attention", attn_flops,
+            [&] { return femasr_window_attention(qkv, rb, ao, B, H, W, C, 8, (b & 1) ? 4 : 0, st); });
         conv(bp + ".attn.proj", ao, T, B, H, W, C, C, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, in, nullptr);
-        if (!tc) run("ln_stats", 0.0, [&] { return femasr_ln_stats(T, mu, rs, (int)M, C, 1e-5f, st); });
+        run("ln_stats", 0.0, [&] { return femasr_ln_stats(T, mu, rs, (int)M, C, 1e-5f, st); });
         conv(bp + ".mlp.fc1", T, hid, B, H, W, C, 4 * C, 1, 1, 0, FEMASR_PRO_LN, mu, rs, P(bp + ".norm2.weight"),
              P(bp + ".norm2.bias"), FEMASR_ACT_GELU, nullptr, nullptr);
         conv(bp + ".mlp.fc2", hid, T, B, H, W, 4 * C, C, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, T, nullptr);
@@ -498,7 +530,20 @@ extern "C" int femasr_net_set_param(femasr_net* net, const char* name, const flo
       DevBuf& tb = net->tcw[key];
       const size_t bytes = femasr_tc_weight_bytes(pi.Cout, pi.Cin, pi.k, pi.k);
       if (!tb.p) { FEMASR_CUDA(cudaMalloc(&tb.p, bytes)); tb.n = bytes / sizeof(float); }
-      return femasr_tc_pack_weight(rb.p, tb.p, pi.Cout, pi.Cin, pi.k, pi.k, st);
+      s = femasr_tc_pack_weight(rb.p, tb.p, pi.Cout, pi.Cin, pi.k, pi.k, st);
+      if (s) return s;
+      // the five nearest-x2 -> conv3x3 sites (femasr_arch.py:172-173, 202-203) also get sub-pixel phase filters
+      const std::string up1 = "multiscale_encoder.blocks." + std::to_string(net->depth + 1) + ".1.weight";
+      const std::string up2 = "multiscale_encoder.blocks." + std::to_string(net->depth + 2) + ".1.weight";
+      const bool is_up = pi.k == 3 && (key == up1 || key == up2 || (key.rfind("decoder_group.", 0) == 0 &&
+                                        key.size() > 15 && key.compare(key.size() - 15, 15, ".block.1.weight") == 0));
+      if (is_up) {
+        DevBuf& ub = net->tcw_up[key];
+        const size_t ubytes = femasr_tc_weight_bytes(4 * pi.Cout, pi.Cin, 2, 2);
+        if (!ub.p) { FEMASR_CUDA(cudaMalloc(&ub.p, ubytes)); ub.n = ubytes / sizeof(float); }
+        return femasr_tc_pack_weight_up2(rb.p, ub.p, pi.Cout, pi.Cin, st);
+      }
+      return FEMASR_OK;
     }
     return FEMASR_OK;
   }

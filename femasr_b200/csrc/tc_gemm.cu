@@ -113,7 +113,9 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
 // ------------------------------------------------------------------------------------------------ kernel
 struct TcP {
   const float* bias; const float* res1; const float* res2; float* y; const float* inv_scale;
+  __half* out_hi; __half* out_lo;   // when set: the result is written as split fp16 planes (next GEMM's A operand)
   int B, H, W, Cin, Cout, taps, act;
+  int up;                        // 1: nearest-x2 upsample + 3x3 conv evaluated as 4 sub-pixel phases of 2x2 taps
   int Wt, Ht, wt_shift;          // 128-pixel tile = Ht rows x Wt cols (Wt power of two)
   int tiles_x, tiles_y, n_tiles; // per image spatial tiles, Cout / BN
   int num_tiles, cchunks;        // total tiles, Cin / 64
@@ -126,7 +128,8 @@ template <int BN>
 struct TcCfg {
   static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * BN * TC_BK * 2;
   static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = 4 * 32 * 36 * 4 /*per-warp 32x32 transpose tiles, row stride 36*/ + 128 * 8 /*row offsets*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators; power of two for BN in {64,128,256}
 };
 
@@ -164,7 +167,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
   const int nkb = p.taps * p.cchunks;
-  const int ksz = p.taps == 9 ? 3 : 1;
+  const int ksz = p.taps == 9 ? 3 : 1;   // (p.up: taps == 4, offsets from the phase)
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -173,19 +176,22 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       const int nt = tile % p.n_tiles;
       int mt = tile / p.n_tiles;
       const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int b = mt / p.tiles_y;
-      const int x0 = tx * p.Wt, y0 = ty * p.Ht, n0 = nt * BN;
+      const int ty = mt % p.tiles_y; mt /= p.tiles_y;
+      const int b = mt % p.B;
+      const int ph = mt / p.B;                       // sub-pixel phase (0 unless p.up)
+      const int py = ph >> 1, px = ph & 1;
+      const int x0 = tx * p.Wt, y0 = ty * p.Ht, n0 = ph * p.Cout + nt * BN;
       for (int kb = 0; kb < nkb; ++kb) {
         const int tap = kb / p.cchunks;
         const int c0 = (kb - tap * p.cchunks) * TC_BK;
-        const int kh = tap / ksz, kw = tap - kh * ksz;
-        const int pad = ksz == 3 ? 1 : 0;
+        int dy = 0, dx = 0;
+        if (p.up) { dy = (tap >> 1) - 1 + py; dx = (tap & 1) - 1 + px; }
+        else if (ksz == 3) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
         mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-        tma_load_4d(sa, &map_a_hi, full_bar(stage), c0, x0 + kw - pad, y0 + kh - pad, b);
-        tma_load_4d(sa + A_PLANE_BYTES, &map_a_lo, full_bar(stage), c0, x0 + kw - pad, y0 + kh - pad, b);
+        tma_load_4d(sa, &map_a_hi, full_bar(stage), c0, x0 + dx, y0 + dy, b);
+        tma_load_4d(sa + A_PLANE_BYTES, &map_a_lo, full_bar(stage), c0, x0 + dx, y0 + dy, b);
         tma_load_2d(sa + 2 * A_PLANE_BYTES, &map_b_hi, full_bar(stage), tap * p.Cin + c0, n0);
         tma_load_2d(sa + 2 * A_PLANE_BYTES + BN * TC_BK * 2, &map_b_lo, full_bar(stage), tap * p.Cin + c0, n0);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -225,19 +231,30 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // TMEM gives each thread one accumulator ROW; a row-per-thread global store would touch 32 different
+    // rows per instruction (half-filled sectors).  Each warp therefore transposes 32x32 chunks through
+    // shared memory and stores with 8 lanes per row x float4 = full 128-byte row segments per instruction.
     const int ew = warp - 4;                    // TMEM lane quarter of this warp (warp_id % 4)
     const int row = ew * 32 + lane;
     const float inv_scale = __ldg(p.inv_scale);
+    const uint32_t epi_base = bar_base + 256;
+    const uint32_t stage_u32 = epi_base + (uint32_t)ew * (32 * 36 * 4);
+    float* stage = reinterpret_cast<float*>(smem_raw + (stage_u32 - smem_u32(smem_raw)));
+    long* rowoff = reinterpret_cast<long*>(smem_raw + (epi_base + 4 * 32 * 36 * 4 - smem_u32(smem_raw))) + ew * 32;
+    const int q = lane & 7, rsub = lane >> 3;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       int mt = tile / p.n_tiles;
       const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int b = mt / p.tiles_y;
+      const int ty = mt % p.tiles_y; mt /= p.tiles_y;
+      const int b = mt % p.B;
+      const int ph = mt / p.B;
       const int y = ty * p.Ht + (row >> p.wt_shift), x = tx * p.Wt + (row & (p.Wt - 1));
       const bool valid = y < p.H && x < p.W;
-      const long off = (((long)b * p.H + y) * p.W + x) * p.Cout + nt * BN;
+      const int oy = p.up ? 2 * y + (ph >> 1) : y, ox = p.up ? 2 * x + (ph & 1) : x;
+      const int Ho = p.up ? 2 * p.H : p.H, Wo = p.up ? 2 * p.W : p.W;
+      rowoff[lane] = valid ? (((long)b * Ho + oy) * Wo + ox) * p.Cout + nt * BN : -1;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
@@ -245,28 +262,51 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       for (int c = 0; c < BN; c += 32) {
         uint32_t r[32];
         tmem_ld32(t_row + (uint32_t)c, r);
-        if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            o.x = __uint_as_float(r[j]) * inv_scale; o.y = __uint_as_float(r[j + 1]) * inv_scale;
-            o.z = __uint_as_float(r[j + 2]) * inv_scale; o.w = __uint_as_float(r[j + 3]) * inv_scale;
-            if (p.bias) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nt * BN + c + j));
-              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-            }
-            if (p.act == FEMASR_ACT_GELU) { o.x = gelu_erf_f(o.x); o.y = gelu_erf_f(o.y); o.z = gelu_erf_f(o.z); o.w = gelu_erf_f(o.w); }
+        for (int j = 0; j < 32; j += 4) {
+          float4 o;
+          o.x = __uint_as_float(r[j]) * inv_scale; o.y = __uint_as_float(r[j + 1]) * inv_scale;
+          o.z = __uint_as_float(r[j + 2]) * inv_scale; o.w = __uint_as_float(r[j + 3]) * inv_scale;
+          if (p.bias) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nt * BN + c + j));
+            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+          }
+          if (p.act == FEMASR_ACT_GELU) { o.x = gelu_erf_f(o.x); o.y = gelu_erf_f(o.y); o.z = gelu_erf_f(o.z); o.w = gelu_erf_f(o.w); }
+          *reinterpret_cast<float4*>(&stage[lane * 36 + j]) = o;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + rsub;
+          long off = rowoff[rr];
+          if (off >= 0) {
+            off += c + 4 * q;
+            float4 o = *reinterpret_cast<const float4*>(&stage[rr * 36 + 4 * q]);
             if (p.res1) {
-              const float4 rv = *reinterpret_cast<const float4*>(p.res1 + off + c + j);
+              const float4 rv = *reinterpret_cast<const float4*>(p.res1 + off);
               o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
             }
             if (p.res2) {
-              const float4 rv = *reinterpret_cast<const float4*>(p.res2 + off + c + j);
+              const float4 rv = *reinterpret_cast<const float4*>(p.res2 + off);
               o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
             }
-            *reinterpret_cast<float4*>(p.y + off + c + j) = o;
+            if (p.out_hi) {
+              const float v[4] = {o.x, o.y, o.z, o.w};
+              __align__(8) __half h[4], l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float cl = fminf(fmaxf(v[e], -65504.f), 65504.f);
+                h[e] = __float2half_rn(cl);
+                l[e] = __float2half_rn(cl - __half2float(h[e]));
+              }
+              *reinterpret_cast<uint2*>(p.out_hi + off) = *reinterpret_cast<const uint2*>(h);
+              *reinterpret_cast<uint2*>(p.out_lo + off) = *reinterpret_cast<const uint2*>(l);
+            } else {
+              *reinterpret_cast<float4*>(p.y + off) = o;
+            }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));             // 128 arrivals release the accumulator
@@ -396,6 +436,29 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, __half* __res
   lo[i] = __float2half_rn(v - __half2float(h));
 }
 
+// nearest-x2 upsample followed by a 3x3 conv == four 2x2 convs on the low-res grid (one per output phase
+// (py,px)), whose weights are sums of the 3x3 taps that land on the same source pixel:
+//   rows: py=0 -> {kh=0 | kh=1,2},  py=1 -> {kh=0,1 | kh=2};  same for columns.  2.25x fewer MACs.
+// out: fp32 [4*Cout][Cin][2][2] (OIHW of the stacked phase filters), summed in a fixed order.
+__global__ void subpixel_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin) {
+  const long n = (long)4 * Cout * Cin * 4;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int bq = (int)(i & 1), a = (int)((i >> 1) & 1);
+  long r = i >> 2;
+  const int ci = (int)(r % Cin); r /= Cin;
+  const int co = (int)(r % Cout);
+  const int ph = (int)(r / Cout);
+  const int py = ph >> 1, px = ph & 1;
+  const int kh0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), kh1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+  const int kw0 = px == 0 ? (bq == 0 ? 0 : 1) : (bq == 0 ? 0 : 2), kw1 = px == 0 ? (bq == 0 ? 0 : 2) : (bq == 0 ? 1 : 2);
+  const float* wp = w + ((long)co * Cin + ci) * 9;
+  float sum = 0.f;
+  for (int kh = kh0; kh <= kh1; ++kh)
+    for (int kw = kw0; kw <= kw1; ++kw) sum += wp[kh * 3 + kw];
+  out[i] = sum;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -476,6 +539,21 @@ extern "C" int femasr_tc_pack_weight(const float* w_oihw, void* blob, int Cout, 
   return launch_status("tc_pack_weight_kernel");
 }
 
+// Packed phase filters for the fused upsample+conv: a blob like femasr_tc_pack_weight's for the stacked
+// [4*Cout][Cin][2][2] filter bank (femasr_tc_weight_bytes(4*Cout, Cin, 2, 2) bytes).
+extern "C" int femasr_tc_pack_weight_up2(const float* w_oihw, void* blob, int Cout, int Cin, void* stream) {
+  FEMASR_CHECK_ARG(w_oihw && blob && Cout > 0 && Cin > 0, "tc_pack_weight_up2: bad argument");
+  cudaStream_t st = as_stream(stream);
+  float* tmp = nullptr;
+  const long n = (long)16 * Cout * Cin;
+  FEMASR_CUDA(cudaMallocAsync(&tmp, n * sizeof(float), st));
+  subpixel_weights_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(w_oihw, tmp, Cout, Cin);
+  int s = launch_status("subpixel_weights_kernel");
+  if (!s) s = femasr_tc_pack_weight(tmp, blob, 4 * Cout, Cin, 2, 2, stream);
+  cudaFreeAsync(tmp, st);
+  return s;
+}
+
 extern "C" int femasr_tc_prepare(const float* x, void* a_hi, void* a_lo, int mode, const float* pro_a, const float* pro_b,
                                  const float* gamma, const float* beta, int B, int H, int W, int C, int upsample,
                                  float eps, void* stream) {
@@ -505,23 +583,29 @@ extern "C" int femasr_tc_prepare(const float* x, void* a_hi, void* a_lo, int mod
 
 // y = act(conv(a) + bias) + res1 + res2 with a given as fp16 hi/lo planes at the conv-input resolution.
 extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
-  FEMASR_CHECK_ARG(a && a->a_hi && a->a_lo && a->w_blob && a->y, "tc_igemm: null pointer");
+  FEMASR_CHECK_ARG(a && a->a_hi && a->a_lo && a->w_blob, "tc_igemm: null pointer");
+  FEMASR_CHECK_ARG(a->y || (a->out_hi && a->out_lo), "tc_igemm: need y or the out_hi/out_lo planes");
+  FEMASR_CHECK_ARG(!a->out_hi == !a->out_lo, "tc_igemm: out_hi and out_lo go together");
   FEMASR_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0, "tc_igemm: empty input");
   FEMASR_CHECK_ARG(a->ksize == 1 || a->ksize == 3, "tc_igemm: ksize must be 1 or 3");
+  FEMASR_CHECK_ARG(!a->upsample || a->ksize == 3, "tc_igemm: upsample fusion needs ksize 3 (and an up2 weight blob)");
   FEMASR_CHECK_ARG(a->Cin % 64 == 0 && a->Cout % 64 == 0, "tc_igemm: Cin and Cout must be multiples of 64");
   int B = a->B, H = a->H, W = a->W;
   if (a->ksize == 1) { W = B * H * W; H = 1; B = 1; }     // pointwise: one long row of tokens
   FEMASR_CHECK_ARG((long)W < (1l << 31), "tc_igemm: too many rows");
-  const int taps = a->ksize * a->ksize;
+  const int taps = a->upsample ? 4 : a->ksize * a->ksize;
+  const int phases = a->upsample ? 4 : 1;
   const long Ktot = (long)taps * a->Cin;
-  const long nw = (long)a->Cout * Ktot;
+  const long nw = (long)phases * a->Cout * Ktot;
   const __half* w_hi = reinterpret_cast<const __half*>(a->w_blob);
   const __half* w_lo = w_hi + nw;
   const float* inv_scale = reinterpret_cast<const float*>(reinterpret_cast<const unsigned int*>(w_lo + nw) + 1);
 
   TcP p;
   p.bias = a->bias; p.res1 = a->res1; p.res2 = a->res2; p.y = a->y; p.inv_scale = inv_scale;
+  p.out_hi = reinterpret_cast<__half*>(a->out_hi); p.out_lo = reinterpret_cast<__half*>(a->out_lo);
   p.B = B; p.H = H; p.W = W; p.Cin = a->Cin; p.Cout = a->Cout; p.taps = taps; p.act = a->act;
+  p.up = a->upsample ? 1 : 0;
   // tile shape: the widest power-of-two Wt <= 128 that wastes the fewest padded pixels
   int best_wt = 8; long best_cost = -1;
   for (int wt = 128; wt >= 8; wt >>= 1) {
@@ -534,7 +618,7 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   p.tiles_x = (int)cdiv(W, p.Wt); p.tiles_y = (int)cdiv(H, p.Ht);
   const int BN = a->Cout % 256 == 0 ? 256 : (a->Cout % 128 == 0 ? 128 : 64);
   p.n_tiles = a->Cout / BN;
-  const long ntile = (long)B * p.tiles_x * p.tiles_y * p.n_tiles;
+  const long ntile = (long)phases * B * p.tiles_x * p.tiles_y * p.n_tiles;
   FEMASR_CHECK_ARG(ntile < (1l << 31), "tc_igemm: too many tiles");
   p.num_tiles = (int)ntile; p.cchunks = a->Cin / 64;
 
@@ -549,7 +633,7 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
     if (s) return s;
   }
   {
-    const cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)a->Cout};
+    const cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)phases * a->Cout};
     const cuuint64_t str[1] = {(cuuint64_t)Ktot * 2};
     const cuuint32_t box[2] = {64, (cuuint32_t)BN};
     int s = make_map(&mbh, w_hi, 2, dims, str, box);

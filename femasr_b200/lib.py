@@ -44,7 +44,8 @@ class TcArgs(C.Structure):
     _fields_ = [("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("w_blob", C.c_void_p), ("bias", C.c_void_p),
                 ("res1", C.c_void_p), ("res2", C.c_void_p), ("y", C.c_void_p),
                 ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
-                ("ksize", C.c_int), ("act", C.c_int)]
+                ("ksize", C.c_int), ("act", C.c_int), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
+                ("upsample", C.c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/femasr_b200.h declares
@@ -72,12 +73,14 @@ SIGNATURES = {
     "femasr_igemm_simt": (_I, [C.POINTER(IgemmArgs), _V]),
     "femasr_tc_weight_bytes": (_Z, [_I, _I, _I, _I]),
     "femasr_tc_pack_weight": (_I, [_V, _V, _I, _I, _I, _I, _V]),
+    "femasr_tc_pack_weight_up2": (_I, [_V, _V, _I, _I, _V]),
     "femasr_tc_prepare": (_I, [_V, _V, _V, _I, _V, _V, _V, _V, _I, _I, _I, _I, _I, _F, _V]),
     "femasr_tc_igemm": (_I, [C.POINTER(TcArgs), _V]),
     "femasr_gn_scratch_floats": (_Z, [_I, _I, _I]),
     "femasr_gn_stats": (_I, [_V, _V, _V, _V, _V, _V, _I, _I, _I, _F, _V]),
     "femasr_ln_stats": (_I, [_V, _V, _V, _I, _I, _F, _V]),
     "femasr_window_attention": (_I, [_V, _V, _V, _I, _I, _I, _I, _I, _I, _V]),
+    "femasr_window_attention_mma": (_I, [_V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _I, _V]),
     "femasr_expand_rel_bias": (_I, [_V, _V, _I, _V]),
     "femasr_row_sumsq": (_I, [_V, _V, _I, _I, _V]),
     "femasr_vq_select": (_I, [_V, _V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _V]),

@@ -154,9 +154,15 @@ typedef struct {
   int B, H, W, Cin, Cout;
   int ksize;               /* 1 or 3 (pad 1) */
   int act;                 /* FEMASR_ACT_* */
+  void* out_hi;            /* optional: write the result as split fp16 NHWC planes (the next GEMM's operand) */
+  void* out_lo;            /*           instead of fp32 y (y may then be NULL) */
+  int upsample;            /* 1: y [B,2H,2W,Cout] = conv3x3(nearest_x2(a)), evaluated as 4 sub-pixel 2x2 convs on the
+                              low-res grid; a_* are at the LOW resolution and w_blob comes from femasr_tc_pack_weight_up2 */
 } femasr_tc_args;
 size_t femasr_tc_weight_bytes(int Cout, int Cin, int kh, int kw);
 int femasr_tc_pack_weight(const float* w_oihw, void* blob, int Cout, int Cin, int kh, int kw, void* stream);
+/* blob of femasr_tc_weight_bytes(4*Cout, Cin, 2, 2) bytes for the upsample-fused form (femasr_tc_args.upsample) */
+int femasr_tc_pack_weight_up2(const float* w_oihw_3x3, void* blob, int Cout, int Cin, void* stream);
 /* mode FEMASR_PRO_NONE | GN_SILU (pro_a/pro_b = scale/shift tables) | LN (gamma/beta, C=256, stats computed
  * in-kernel).  x fp32 NHWC [B,H,W,C] -> a_hi/a_lo fp16 NHWC [B,H*u,W*u,C], u = upsample ? 2 : 1. */
 int femasr_tc_prepare(const float* x, void* a_hi, void* a_lo, int mode, const float* pro_a, const float* pro_b,
@@ -180,6 +186,10 @@ int femasr_ln_stats(const float* x, float* mean, float* rstd, int M, int C, floa
  * bias_full [heads][64][64] = relative_position_bias_table[relative_position_index] (:127-129). */
 int femasr_window_attention(const float* qkv, const float* bias_full, float* out, int B, int H, int W,
                             int C, int heads, int shift, void* stream);
+/* Same contract on warp-level tensor cores (mma.sync m16n8k16, 3-term split-fp16, fp32 softmax). */
+int femasr_window_attention_mma(const float* qkv, const float* bias_full, float* out, void* out_hi, void* out_lo,
+                                int B, int H, int W, int C, int heads, int shift, void* stream);
+/* (out_hi/out_lo non-NULL: the result is written as split fp16 planes [B*H*W, C] instead of fp32 `out`) */
 int femasr_expand_rel_bias(const float* table /*[225,heads]*/, float* bias_full, int heads, void* stream);
 
 /* VectorQuantizer.forward (femasr_arch.py:50-100) given zc = z @ codebook^T:

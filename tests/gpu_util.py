@@ -86,11 +86,26 @@ def tc_prepare(x_nhwc, mode=0, pro_a=None, pro_b=None, gamma=None, beta=None, up
     return hi, lo
 
 
-def tc_igemm(hi, lo, blob, bias, Cout, ksize=3, act=0, res1=None, res2=None, y=None):
+def tc_pack_up2(w_oihw):
+    lib = L.load()
+    co, ci, _, _ = w_oihw.shape
+    blob = torch.empty(lib.femasr_tc_weight_bytes(4 * co, ci, 2, 2), dtype=torch.uint8, device=w_oihw.device)
+    w = w_oihw.contiguous()
+    L.check(lib.femasr_tc_pack_weight_up2(p(w), p(blob), co, ci, S()))
+    return blob
+
+
+def tc_igemm(hi, lo, blob, bias, Cout, ksize=3, act=0, res1=None, res2=None, y=None, upsample=0, split_out=False):
     lib = L.load()
     B, H, W, Cin = hi.shape
-    if y is None:
-        y = torch.empty(B, H, W, Cout, device=hi.device)
-    a = L.TcArgs(p(hi), p(lo), p(blob), p(bias), p(res1), p(res2), p(y), B, H, W, Cin, Cout, ksize, act)
+    u = 2 if upsample else 1
+    oh = ol = None
+    if split_out:
+        oh = torch.empty(B, H * u, W * u, Cout, dtype=torch.float16, device=hi.device)
+        ol = torch.empty_like(oh)
+    elif y is None:
+        y = torch.empty(B, H * u, W * u, Cout, device=hi.device)
+    a = L.TcArgs(p(hi), p(lo), p(blob), p(bias), p(res1), p(res2), p(y), B, H, W, Cin, Cout, ksize, act,
+                 p(oh), p(ol), upsample)
     L.check(lib.femasr_tc_igemm(C.byref(a), S()))
-    return y
+    return (oh, ol) if split_out else y

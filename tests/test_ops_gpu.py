@@ -115,6 +115,13 @@ def test_window_attention(cuda, H, W, shift):
     qkvg = qkv.to(cuda)
     L.check(lib.femasr_window_attention(qkvg.data_ptr(), full.data_ptr(), out.data_ptr(), B, H, W, Cc, 8, shift, G.S()))
     close(out, want, 2e-5, "window attention")
+    out2 = torch.zeros(B, H * W, Cc, device=cuda)
+    L.check(lib.femasr_window_attention_mma(qkvg.data_ptr(), full.data_ptr(), out2.data_ptr(), None, None, B, H, W, Cc, 8, shift, G.S()))
+    close(out2, want, 2e-5, "window attention (mma.sync split-fp16)")
+    oh = torch.zeros(B, H * W, Cc, dtype=torch.float16, device=cuda)
+    ol = torch.zeros_like(oh)
+    L.check(lib.femasr_window_attention_mma(qkvg.data_ptr(), full.data_ptr(), None, oh.data_ptr(), ol.data_ptr(), B, H, W, Cc, 8, shift, G.S()))
+    close(oh.float() + ol.float(), want, 2e-5, "window attention (split fp16 planes out)")
 
 
 @pytest.mark.parametrize("e_dim,init", [(256, "tiny"), (512, "tiny"), (256, "wide")])

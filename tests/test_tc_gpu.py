@@ -58,6 +58,29 @@ def test_tc_conv3x3(cuda, B, H, W, Cin, Cout):
     assert e <= 2e-5, f"tensor-core conv rel err {e:.3e} vs fp32 {f32:.3e}"
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 8, 256, 256), (2, 12, 20, 256, 128), (1, 33, 9, 128, 64)])
+def test_tc_upsample_conv_subpixel(cuda, B, H, W, Cin, Cout):
+    """nearest x2 -> conv3x3 evaluated as four 2x2 sub-pixel convs on the low-res grid."""
+    x, w, b = rnd(B, Cin, H, W, seed=20), rnd(Cout, Cin, 3, 3, seed=21, scale=0.03), rnd(Cout, seed=22)
+    res = rnd(B, Cout, 2 * H, 2 * W, seed=23)
+    want = F.conv2d(O.upsample2(x).double(), w.double(), b.double(), padding=1) + res.double()
+    hi, lo = G.tc_prepare(G.nhwc(x).to(cuda))
+    y = G.tc_igemm(hi, lo, G.tc_pack_up2(w.to(cuda)), b.to(cuda), Cout, 3, upsample=1, res1=G.nhwc(res).to(cuda))
+    e = rel_err(G.nchw(y), want)
+    print(f"tc up-conv {B}x{H}x{W} {Cin}->{Cout}: rel err {e:.2e}")
+    assert e <= 2e-5
+
+
+def test_tc_split_output(cuda):
+    M, K, N = 500, 256, 1024
+    x, w, b = rnd(M, K, seed=24), rnd(N, K, seed=25, scale=0.05), rnd(N, seed=26)
+    want = F.gelu(F.linear(x.double(), w.double(), b.double()))
+    hi, lo = G.tc_prepare(x.view(1, 1, M, K).to(cuda))
+    oh, ol = G.tc_igemm(hi, lo, G.tc_pack(w.view(N, K, 1, 1).to(cuda)), b.to(cuda), N, 1, act=1, split_out=True)
+    got = (oh.float() + ol.float()).view(M, N)
+    assert rel_err(got, want) <= 1e-5
+
+
 @pytest.mark.parametrize("M,K,N,act", [(300, 256, 768, 0), (1000, 256, 1024, 1), (257, 1024, 256, 0), (4096, 256, 256, 0)])
 def test_tc_linear(cuda, M, K, N, act):
     x, w, b = rnd(M, K, seed=5), rnd(N, K, seed=6, scale=0.05), rnd(N, seed=7)
