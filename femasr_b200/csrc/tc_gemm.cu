@@ -7,14 +7,15 @@
 // i.e. ~22 significand bits per operand; the dropped a_lo*w_lo term is ~2^-22 relative (SURVEY 7.3-1:
 // the path needs >=18 bits before the VQ and >=13 after it; single-pass fp16/bf16/tf32 fails parity).
 //
-// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
 //   warp 0  TMA producer: activation tile = 4-D box (64 ch x Wt x Ht x 1) of the NHWC fp16 planes at the
 //           tap offset (kh-1, kw-1) - out-of-bounds rows/cols are zero-filled by TMA, which IS the conv
 //           padding - and the weight tile = 2-D box (64 x BN) of the K-major fp16 planes; 128B swizzle.
 //   warp 1  MMA issuer (one elected thread): 4 k-steps x 3 split products per 64-wide k-block into a
 //           128 x BN fp32 accumulator in TMEM (two accumulators: the epilogue of tile i overlaps tile i+1).
 //   warp 2  TMEM allocator.
-//   warps 4-7  epilogue: tcgen05.ld 32 columns at a time -> *2^-s + bias -> GELU -> + residual(s) -> fp32 NHWC.
+//   warps 4-11 epilogue: tcgen05.ld 16 columns at a time -> *2^-s + bias -> GELU -> smem transpose ->
+//           + prefetched residual(s) -> coalesced fp32 NHWC (or split-fp16 plane) stores.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -128,13 +129,13 @@ template <int BN>
 struct TcCfg {
   static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * BN * TC_BK * 2;
   static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
-  static constexpr int EPI_BYTES = 4 * 32 * 36 * 4 /*per-warp 32x32 transpose tiles, row stride 36*/ + 128 * 8 /*row offsets*/;
+  static constexpr int EPI_BYTES = 8 * 2048 /*per-warp 32x16 fp32 transpose tiles*/ + 8 * 32 * 8 /*row offsets*/;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators; power of two for BN in {64,128,256}
 };
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcP p) {
   using Cfg = TcCfg<BN>;
@@ -152,7 +153,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -230,18 +231,23 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    // TMEM gives each thread one accumulator ROW; a row-per-thread global store would touch 32 different
-    // rows per instruction (half-filled sectors).  Each warp therefore transposes 32x32 chunks through
-    // shared memory and stores with 8 lanes per row x float4 = full 128-byte row segments per instruction.
-    const int ew = warp - 4;                    // TMEM lane quarter of this warp (warp_id % 4)
+    // ===================== epilogue (8 warps) =====================
+    // TMEM hands each thread one accumulator ROW; storing rows per thread would touch 32 different rows per
+    // instruction.  Each warp therefore transposes 32x16 chunks through (XOR-swizzled) shared memory and
+    // stores with 4 lanes per row x float4: full 64-byte row segments, 8 rows per instruction.
+    // Warps 4-7 take the left half of the accumulator columns, warps 8-11 the right half (TMEM lane quarter
+    // = warp_id % 4).  Residual tiles are software-prefetched one chunk ahead so their latency overlaps the
+    // TMEM load / math of the current chunk (the stores may alias the residual, which otherwise pins every load
+    // behind the previous store).
+    const int e = warp - 4;
+    const int ew = e & 3, half = e >> 2;
     const int row = ew * 32 + lane;
     const float inv_scale = __ldg(p.inv_scale);
     const uint32_t epi_base = bar_base + 256;
-    const uint32_t stage_u32 = epi_base + (uint32_t)ew * (32 * 36 * 4);
-    float* stage = reinterpret_cast<float*>(smem_raw + (stage_u32 - smem_u32(smem_raw)));
-    long* rowoff = reinterpret_cast<long*>(smem_raw + (epi_base + 4 * 32 * 36 * 4 - smem_u32(smem_raw))) + ew * 32;
-    const int q = lane & 7, rsub = lane >> 3;
+    float* stage = reinterpret_cast<float*>(smem_raw + (epi_base + (uint32_t)e * 2048u - smem_u32(smem_raw)));
+    long* rowoff = reinterpret_cast<long*>(smem_raw + (epi_base + 8u * 2048u - smem_u32(smem_raw))) + e * 32;
+    const int q = lane & 3, rsub = lane >> 2;
+    constexpr int CH = 16, NCH = BN / 2 / CH;       // chunks per warp
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
@@ -254,38 +260,56 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       const bool valid = y < p.H && x < p.W;
       const int oy = p.up ? 2 * y + (ph >> 1) : y, ox = p.up ? 2 * x + (ph & 1) : x;
       const int Ho = p.up ? 2 * p.H : p.H, Wo = p.up ? 2 * p.W : p.W;
-      rowoff[lane] = valid ? (((long)b * Ho + oy) * Wo + ox) * p.Cout + nt * BN : -1;
+      const int col0 = nt * BN + half * (BN / 2);
+      rowoff[lane] = valid ? (((long)b * Ho + oy) * Wo + ox) * p.Cout + col0 : -1;
+      __syncwarp();
+      long offs[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) { const long o = rowoff[it * 8 + rsub]; offs[it] = o < 0 ? -1 : o + 4 * q; }
+      float4 cur[4], nxt[4];
+      if (p.res1) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+          cur[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.res1 + offs[it]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_row + (uint32_t)c, r);
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int c = ci * CH;
+        if (p.res1 && ci + 1 < NCH) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+          for (int it = 0; it < 4; ++it)
+            nxt[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.res1 + offs[it] + c + CH) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(t_row + (uint32_t)c) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
           float4 o;
-          o.x = __uint_as_float(r[j]) * inv_scale; o.y = __uint_as_float(r[j + 1]) * inv_scale;
-          o.z = __uint_as_float(r[j + 2]) * inv_scale; o.w = __uint_as_float(r[j + 3]) * inv_scale;
+          o.x = __uint_as_float(r[4 * j]) * inv_scale; o.y = __uint_as_float(r[4 * j + 1]) * inv_scale;
+          o.z = __uint_as_float(r[4 * j + 2]) * inv_scale; o.w = __uint_as_float(r[4 * j + 3]) * inv_scale;
           if (p.bias) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nt * BN + c + j));
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c + 4 * j));
             o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
           }
           if (p.act == FEMASR_ACT_GELU) { o.x = gelu_erf_f(o.x); o.y = gelu_erf_f(o.y); o.z = gelu_erf_f(o.z); o.w = gelu_erf_f(o.w); }
-          *reinterpret_cast<float4*>(&stage[lane * 36 + j]) = o;
+          *reinterpret_cast<float4*>(&stage[lane * 16 + 4 * (j ^ ((lane >> 1) & 3))]) = o;
         }
         __syncwarp();
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + rsub;
-          long off = rowoff[rr];
-          if (off >= 0) {
-            off += c + 4 * q;
-            float4 o = *reinterpret_cast<const float4*>(&stage[rr * 36 + 4 * q]);
-            if (p.res1) {
-              const float4 rv = *reinterpret_cast<const float4*>(p.res1 + off);
-              o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-            }
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + rsub;
+          if (offs[it] >= 0) {
+            const long off = offs[it] + c;
+            float4 o = *reinterpret_cast<const float4*>(&stage[rr * 16 + 4 * (q ^ ((rr >> 1) & 3))]);
+            if (p.res1) { o.x += cur[it].x; o.y += cur[it].y; o.z += cur[it].z; o.w += cur[it].w; }
             if (p.res2) {
               const float4 rv = *reinterpret_cast<const float4*>(p.res2 + off);
               o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
@@ -294,10 +318,10 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
               const float v[4] = {o.x, o.y, o.z, o.w};
               __align__(8) __half h[4], l[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float cl = fminf(fmaxf(v[e], -65504.f), 65504.f);
-                h[e] = __float2half_rn(cl);
-                l[e] = __float2half_rn(cl - __half2float(h[e]));
+              for (int k = 0; k < 4; ++k) {
+                const float cl = fminf(fmaxf(v[k], -65504.f), 65504.f);
+                h[k] = __float2half_rn(cl);
+                l[k] = __float2half_rn(cl - __half2float(h[k]));
               }
               *reinterpret_cast<uint2*>(p.out_hi + off) = *reinterpret_cast<const uint2*>(h);
               *reinterpret_cast<uint2*>(p.out_lo + off) = *reinterpret_cast<const uint2*>(l);
@@ -307,9 +331,11 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           }
         }
         __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));             // 128 arrivals release the accumulator
+      mbar_arrive(tempty_bar(acc));             // 256 arrivals release the accumulator
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -510,7 +536,7 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
     attr_set = true;
   }
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  tc_igemm_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
+  tc_igemm_kernel<BN><<<grid, 384, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
   return launch_status("tc_igemm_kernel");
 }
 

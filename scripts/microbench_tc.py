@@ -1,0 +1,62 @@
+"""Per-shape timing of the tensor-core implicit GEMM through the C ABI (CUDA events, L2 flushed between reps).
+Usage (GPU box): python scripts/microbench_tc.py > gpurun_out/microbench.txt"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tests import gpu_util as G  # noqa: E402
+
+dev = torch.device("cuda", 0)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, reps=5):
+    fn(); fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def conv_case(name, B, H, W, Cin, Cout, ksize=3, up=0, res=False, act=0, split=False, bias=True):
+    hi = (torch.randn(B, H, W, Cin, device=dev) * 0.5).half()
+    lo = (torch.randn(B, H, W, Cin, device=dev) * 1e-4).half()
+    w = torch.randn(Cout, Cin, ksize, ksize, device=dev) * 0.03
+    blob = G.tc_pack_up2(w) if up else G.tc_pack(w)
+    b = torch.randn(Cout, device=dev) if bias else None
+    u = 2 if up else 1
+    y = None if split else torch.empty(B, H * u, W * u, Cout, device=dev)
+    r = torch.randn(B, H * u, W * u, Cout, device=dev) if res else None
+    fn = lambda: G.tc_igemm(hi, lo, blob, b, Cout, ksize, act=act, res1=r, y=y, upsample=up, split_out=split)
+    ms = timeit(fn)
+    flops = 2.0 * B * H * u * W * u * Cout * Cin * ksize * ksize
+    execd = 3 * 2.0 * B * H * W * Cout * Cin * (4 * 4 if up else ksize * ksize)
+    print(f"{name:34s} {ms:8.3f} ms  algorithmic {flops / ms / 1e9:7.1f} TF/s  executed {execd / ms / 1e9:7.1f} TF/s")
+    return ms
+
+
+M = 32 * 64 * 64
+print("# Swin linears (tokens = 131072)")
+conv_case("qkv 256->768", 1, 1, M, 256, 768, 1)
+conv_case("proj 256->256 +res", 1, 1, M, 256, 256, 1, res=True)
+conv_case("fc1 256->1024 gelu fp32 out", 1, 1, M, 256, 1024, 1, act=1)
+conv_case("fc1 256->1024 gelu split out", 1, 1, M, 256, 1024, 1, act=1, split=True)
+conv_case("fc1 256->1024 noact fp32 out", 1, 1, M, 256, 1024, 1, act=0)
+conv_case("fc2 1024->256 +res", 1, 1, M, 1024, 256, 1, res=True)
+print("# 3x3 convs, batch 32")
+conv_case("conv 256->256 @64x64 +res", 32, 64, 64, 256, 256, res=True)
+conv_case("conv 256->256 @128x128 +res", 32, 128, 128, 256, 256, res=True)
+conv_case("conv 128->128 @256x256 +res", 32, 256, 256, 128, 128, res=True)
+conv_case("conv 64->64 @512x512 +res", 32, 512, 512, 64, 64, res=True)
+conv_case("conv 64->64 @512x512", 32, 512, 512, 64, 64)
+print("# upsample-fused (sub-pixel) convs, low-res input size given")
+conv_case("up 256->256 @64->128", 32, 64, 64, 256, 256, up=1)
+conv_case("up 256->128 @128->256", 32, 128, 128, 256, 128, up=1)
+conv_case("up 128->64 @256->512", 32, 256, 256, 128, 64, up=1)
