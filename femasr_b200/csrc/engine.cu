@@ -260,7 +260,7 @@ struct Ctx {
   void conv_tc(const std::string& wname, const float* x, float* y, int B, int Hin, int Win, int Cin, int Cout, int ksize,
                int upsample, int prologue, const float* pa, const float* pb, const float* gamma, const float* beta,
                int act, const float* res1, const float* res2, const void* pre_hi = nullptr, const void* pre_lo = nullptr,
-               void* out_hi = nullptr, void* out_lo = nullptr) {
+               void* out_hi = nullptr, void* out_lo = nullptr, float* gn_partial = nullptr) {
     const size_t plane_halves = (size_t)B * Hin * Win * Cin;
     float *ahi = nullptr, *alo = nullptr;
     if (!pre_hi) {
@@ -278,7 +278,7 @@ struct Ctx {
       t.a_hi = pre_hi ? pre_hi : ahi; t.a_lo = pre_hi ? pre_lo : alo;
       t.w_blob = upsample ? net->tcw_up[wname + ".weight"].p : net->tcw[wname + ".weight"].p;
       t.bias = P(wname + ".bias");
-      t.res1 = res1; t.res2 = res2; t.y = y; t.out_hi = out_hi; t.out_lo = out_lo;
+      t.res1 = res1; t.res2 = res2; t.y = y; t.out_hi = out_hi; t.out_lo = out_lo; t.gn_partial = gn_partial;
       t.B = B; t.H = Hin; t.W = Win; t.Cin = Cin; t.Cout = Cout; t.ksize = ksize; t.act = act; t.upsample = upsample;
       const int u = upsample ? 2 : 1;
       const double flops = 2.0 * B * (Hin * u) * (double)(Win * u) * Cout * Cin * ksize * ksize;   // algorithmic (reference) count
@@ -295,27 +295,73 @@ struct Ctx {
     run("gn_stats", 0.0, [&] { return femasr_gn_stats(x, gw, gb, sc, sh, scratch, B, HW, C, 1e-6f, st); });
   }
 
+  // GroupNorm partial sums produced by a tensor-core conv epilogue (see femasr_tc_args.gn_partial)
+  struct Stats { float* partial = nullptr; int rows = 0; };
+  Stats alloc_stats(int B, int H, int W, int upsample) {     // H,W: conv-input (low-res if upsample) size
+    Stats st_;
+    st_.rows = femasr_tc_gn_partial_rows(H, W, upsample);
+    st_.partial = ar.alloc((size_t)B * st_.rows * 32 * 2);
+    return st_;
+  }
+  bool tc_convs(int C) const { return net->cfg.gemm_path == 1 && C % 64 == 0; }
+
+  // scale/shift tables for `norm` applied to x: from epilogue partials when available, else a stats pass over x
+  void gn_tables(const std::string& norm, const float* x, const Stats& sx, float* sc, float* sh, int B, int HW, int C) {
+    if (sx.partial) {
+      if (dry() || !ok()) return;
+      const float *gw = P(norm + ".weight"), *gb = P(norm + ".bias");
+      run("gn_finalize_rows", 0.0, [&] { return femasr_gn_finalize_rows(sx.partial, gw, gb, sc, sh, B, sx.rows, HW, C, 1e-6f, st); });
+    } else {
+      float* scratch = ar.alloc(femasr_gn_scratch_floats(B, HW, C));
+      gn(norm, x, sc, sh, scratch, B, HW, C);
+      ar.release(scratch);
+    }
+  }
+
   // fema_utils.py:65-84, in place on x; optional extra residual added after the block (encoder skip).
-  void resblock(const std::string& p, float* x, int B, int H, int W, int C, const float* extra) {
+  // sx: GroupNorm partials of x from its producer (consumed/released here); returns the partials of the block's
+  // output when want_out (for the next ResBlock's first norm), which the caller releases after use.
+  Stats resblock(const std::string& p, float* x, int B, int H, int W, int C, const float* extra, Stats sx, bool want_out) {
     const size_t n = (size_t)B * H * W * C;
+    const bool tc = tc_convs(C);
     float* sc = ar.alloc((size_t)B * C);
     float* sh = ar.alloc((size_t)B * C);
-    float* scratch = ar.alloc(femasr_gn_scratch_floats(B, H * W, C));
     float* t = ar.alloc(n);
-    gn(p + ".conv.0.norm", x, sc, sh, scratch, B, H * W, C);
-    conv(p + ".conv.2", x, t, B, H, W, C, C, 3, 1, 0, FEMASR_PRO_GN_SILU, sc, sh, nullptr, nullptr, 0, nullptr, nullptr);
-    gn(p + ".conv.3.norm", t, sc, sh, scratch, B, H * W, C);
-    conv(p + ".conv.5", t, x, B, H, W, C, C, 3, 1, 0, FEMASR_PRO_GN_SILU, sc, sh, nullptr, nullptr, 0, x, extra);
-    ar.release(t); ar.release(scratch); ar.release(sh); ar.release(sc);
+    gn_tables(p + ".conv.0.norm", x, sx, sc, sh, B, H * W, C);
+    if (sx.partial) ar.release(sx.partial);
+    Stats s1, s2;
+    if (tc) s1 = alloc_stats(B, H, W, 0);
+    if (tc)
+      conv_tc(p + ".conv.2", x, t, B, H, W, C, C, 3, 0, FEMASR_PRO_GN_SILU, sc, sh, nullptr, nullptr, 0, nullptr, nullptr,
+              nullptr, nullptr, nullptr, nullptr, s1.partial);
+    else
+      conv(p + ".conv.2", x, t, B, H, W, C, C, 3, 1, 0, FEMASR_PRO_GN_SILU, sc, sh, nullptr, nullptr, 0, nullptr, nullptr);
+    gn_tables(p + ".conv.3.norm", t, s1, sc, sh, B, H * W, C);
+    if (s1.partial) ar.release(s1.partial);
+    if (tc && want_out) s2 = alloc_stats(B, H, W, 0);
+    if (tc)
+      conv_tc(p + ".conv.5", t, x, B, H, W, C, C, 3, 0, FEMASR_PRO_GN_SILU, sc, sh, nullptr, nullptr, 0, x, extra,
+              nullptr, nullptr, nullptr, nullptr, s2.partial);
+    else
+      conv(p + ".conv.5", t, x, B, H, W, C, C, 3, 1, 0, FEMASR_PRO_GN_SILU, sc, sh, nullptr, nullptr, 0, x, extra);
+    ar.release(t); ar.release(sh); ar.release(sc);
+    return s2;
   }
 
   // nn.Upsample(2) -> conv3x3 -> ResBlock -> ResBlock  (femasr_arch.py:168-180, 195-211); returns new buffer
   float* up_block(const std::string& pconv, const std::string& prb1, const std::string& prb2, const float* x, int B,
                   int H, int W, int Cin, int Cout, const float* extra) {
     float* y = ar.alloc((size_t)B * 2 * H * 2 * W * Cout);
-    conv(pconv, x, y, B, H, W, Cin, Cout, 3, 1, 1, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
-    resblock(prb1, y, B, 2 * H, 2 * W, Cout, nullptr);
-    resblock(prb2, y, B, 2 * H, 2 * W, Cout, extra);
+    Stats s0;
+    if (tc_convs(Cin) && tc_convs(Cout) && (dry() || net->tcw_up.count(pconv + ".weight"))) {
+      s0 = alloc_stats(B, H, W, 1);
+      conv_tc(pconv, x, y, B, H, W, Cin, Cout, 3, 1, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
+              nullptr, nullptr, nullptr, nullptr, s0.partial);
+    } else {
+      conv(pconv, x, y, B, H, W, Cin, Cout, 3, 1, 1, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
+    }
+    Stats s1 = resblock(prb1, y, B, 2 * H, 2 * W, Cout, nullptr, s0, true);
+    resblock(prb2, y, B, 2 * H, 2 * W, Cout, extra, s1, false);
     return y;
   }
 
@@ -415,8 +461,8 @@ struct Ctx {
       conv(b + ".0", cur, nxt, B, h, w, c, co, 3, 2, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
       ar.release(cur);
       cur = nxt; h = ho; w = wo; c = co;
-      resblock(b + ".1", cur, B, h, w, c, nullptr);
-      resblock(b + ".2", cur, B, h, w, c, nullptr);
+      Stats sd = resblock(b + ".1", cur, B, h, w, c, nullptr, Stats(), true);
+      resblock(b + ".2", cur, B, h, w, c, nullptr, sd, false);
     }
     tap("down", cur, (size_t)B * h * w * c);
     swin(enc + ".blocks." + std::to_string(d), cur, B, h, w);

@@ -70,6 +70,32 @@ __global__ void gn_finalize_kernel(const double* __restrict__ partial, const flo
   }
 }
 
+// Same, from the fp32 partial rows the tensor-core conv epilogue wrote: partial[b][row][g][2].
+__global__ void gn_finalize_rows_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, float* __restrict__ scale,
+                                        float* __restrict__ shift, int HW, int C, int rows, float eps) {
+  const int b = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double a = 0.0, a2 = 0.0;
+  for (int r = lane; r < rows; r += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(partial + (((long)b * rows + r) * GN_GROUPS + g) * 2);
+    a += (double)v.x; a2 += (double)v.y;
+  }
+  a = warp_sum_d(a); a2 = warp_sum_d(a2);
+  const int cpg = C / GN_GROUPS;
+  const double n = (double)HW * cpg;
+  const double mean = a / n;
+  double var = a2 / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float meanf = (float)mean;
+  if (lane < cpg) {
+    const int c = g * cpg + lane;
+    const float sc = rstd * gamma[c];
+    scale[(long)b * C + c] = sc;
+    shift[(long)b * C + c] = fmaf(-sc, meanf, beta[c]);
+  }
+}
+
 // one warp per row of 256 channels: two-pass mean / variance in registers.
 __global__ void __launch_bounds__(256) ln_stats_kernel(const float* __restrict__ x, float* __restrict__ mean,
                                                        float* __restrict__ rstd, long M, float eps) {
@@ -114,6 +140,14 @@ extern "C" int femasr_gn_stats(const float* x, const float* gamma, const float* 
   if (st) return st;
   gn_finalize_kernel<<<B, GN_GROUPS * 32, 0, as_stream(stream)>>>(partial, gamma, beta, scale, shift, HW, C, nchunks, eps);
   return launch_status("gn_finalize_kernel");
+}
+
+extern "C" int femasr_gn_finalize_rows(const float* partial, const float* gamma, const float* beta, float* scale,
+                                       float* shift, int B, int rows, int HW, int C, float eps, void* stream) {
+  FEMASR_CHECK_ARG(partial && gamma && beta && scale && shift, "gn_finalize_rows: null pointer");
+  FEMASR_CHECK_ARG(B > 0 && rows > 0 && HW > 0 && (C == 64 || C == 128 || C == 256), "gn_finalize_rows: bad shape");
+  gn_finalize_rows_kernel<<<B, GN_GROUPS * 32, 0, as_stream(stream)>>>(partial, gamma, beta, scale, shift, HW, C, rows, eps);
+  return launch_status("gn_finalize_rows_kernel");
 }
 
 extern "C" int femasr_ln_stats(const float* x, float* mean, float* rstd, int M, int C, float eps, void* stream) {

@@ -115,6 +115,8 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
 struct TcP {
   const float* bias; const float* res1; const float* res2; float* y; const float* inv_scale;
   __half* out_hi; __half* out_lo;   // when set: the result is written as split fp16 planes (next GEMM's A operand)
+  float* gn_partial;                // when set: per-(image, tile, lane-quarter) GroupNorm partial sums of the OUTPUT
+  int gn_rows, cpg;                 // partial rows per image; channels per group (Cout / 32)
   int B, H, W, Cin, Cout, taps, act;
   int up;                        // 1: nearest-x2 upsample + 3x3 conv evaluated as 4 sub-pixel phases of 2x2 taps
   int Wt, Ht, wt_shift;          // 128-pixel tile = Ht rows x Wt cols (Wt power of two)
@@ -303,6 +305,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           *reinterpret_cast<float4*>(&stage[lane * 16 + 4 * (j ^ ((lane >> 1) & 3))]) = o;
         }
         __syncwarp();
+        float sa = 0.f, ssa = 0.f, sb = 0.f, ssb = 0.f;   // GroupNorm partials of channels (x,y) and (z,w)
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int rr = it * 8 + rsub;
@@ -314,6 +317,8 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
               const float4 rv = *reinterpret_cast<const float4*>(p.res2 + off);
               o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
             }
+            sa += o.x + o.y; ssa = fmaf(o.x, o.x, fmaf(o.y, o.y, ssa));
+            sb += o.z + o.w; ssb = fmaf(o.z, o.z, fmaf(o.w, o.w, ssb));
             if (p.out_hi) {
               const float v[4] = {o.x, o.y, o.z, o.w};
               __align__(8) __half h[4], l[4];
@@ -327,6 +332,29 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
               *reinterpret_cast<uint2*>(p.out_lo + off) = *reinterpret_cast<const uint2*>(l);
             } else {
               *reinterpret_cast<float4*>(p.y + off) = o;
+            }
+          }
+        }
+        if (p.gn_partial) {
+          // fixed-order reduction over the warp's 32 rows (lanes sharing q), then one partial per group
+#pragma unroll
+          for (int o = 4; o <= 16; o <<= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o); ssa += __shfl_xor_sync(0xffffffffu, ssa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o); ssb += __shfl_xor_sync(0xffffffffu, ssb, o);
+          }
+          const int tile_in_img = (ph * p.tiles_y + ty) * p.tiles_x + tx;
+          float* gp = p.gn_partial + (((long)b * p.gn_rows + tile_in_img * 4 + ew) * 32) * 2;
+          const int ch0 = col0 + c;                      // first channel of this chunk
+          if (p.cpg == 8) {
+            float s1 = sa + sb, s2 = ssa + ssb;
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+            if (lane == 0 || lane == 2) *reinterpret_cast<float2*>(gp + (ch0 / 8 + (lane >> 1)) * 2) = make_float2(s1, s2);
+          } else if (p.cpg == 4) {
+            if (lane < 4) *reinterpret_cast<float2*>(gp + (ch0 / 4 + lane) * 2) = make_float2(sa + sb, ssa + ssb);
+          } else {
+            if (lane < 4) {
+              *reinterpret_cast<float2*>(gp + (ch0 / 2 + 2 * lane) * 2) = make_float2(sa, ssa);
+              *reinterpret_cast<float2*>(gp + (ch0 / 2 + 2 * lane + 1) * 2) = make_float2(sb, ssb);
             }
           }
         }
@@ -544,6 +572,23 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
 
 using namespace femasr;
 
+static void tc_tile_shape(int H, int W, int* Wt, int* Ht) {
+  int best_wt = 8; long best_cost = -1;
+  for (int wt = 128; wt >= 8; wt >>= 1) {
+    const int ht = 128 / wt;
+    const long cost = cdiv(W, wt) * wt * cdiv(H, ht) * ht;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_wt = wt; }
+  }
+  *Wt = best_wt; *Ht = 128 / best_wt;
+}
+
+// rows of GroupNorm partials femasr_tc_igemm writes per image for a conv on an [H,W] (low-res if upsample) input
+extern "C" int femasr_tc_gn_partial_rows(int H, int W, int upsample) {
+  int wt, ht;
+  tc_tile_shape(H, W, &wt, &ht);
+  return (upsample ? 4 : 1) * (int)cdiv(W, wt) * (int)cdiv(H, ht) * 4;
+}
+
 extern "C" size_t femasr_tc_weight_bytes(int Cout, int Cin, int kh, int kw) {
   return (size_t)2 * Cout * Cin * kh * kw * sizeof(__half) + 256;   // hi plane, lo plane, then {absmax, inv_scale}
 }
@@ -630,16 +675,13 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   TcP p;
   p.bias = a->bias; p.res1 = a->res1; p.res2 = a->res2; p.y = a->y; p.inv_scale = inv_scale;
   p.out_hi = reinterpret_cast<__half*>(a->out_hi); p.out_lo = reinterpret_cast<__half*>(a->out_lo);
+  p.gn_partial = a->gn_partial; p.cpg = a->Cout / 32; p.gn_rows = 0;
+  FEMASR_CHECK_ARG(!a->gn_partial || (a->ksize == 3 && (a->Cout == 64 || a->Cout == 128 || a->Cout == 256)),
+                   "tc_igemm: gn_partial needs a 3x3 conv with Cout in {64,128,256}");
   p.B = B; p.H = H; p.W = W; p.Cin = a->Cin; p.Cout = a->Cout; p.taps = taps; p.act = a->act;
   p.up = a->upsample ? 1 : 0;
   // tile shape: the widest power-of-two Wt <= 128 that wastes the fewest padded pixels
-  int best_wt = 8; long best_cost = -1;
-  for (int wt = 128; wt >= 8; wt >>= 1) {
-    const int ht = 128 / wt;
-    const long cost = cdiv(W, wt) * wt * cdiv(H, ht) * ht;
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_wt = wt; }
-  }
-  p.Wt = best_wt; p.Ht = 128 / best_wt;
+  tc_tile_shape(H, W, &p.Wt, &p.Ht);
   p.wt_shift = 0; while ((1 << p.wt_shift) < p.Wt) ++p.wt_shift;
   p.tiles_x = (int)cdiv(W, p.Wt); p.tiles_y = (int)cdiv(H, p.Ht);
   const int BN = a->Cout % 256 == 0 ? 256 : (a->Cout % 128 == 0 ? 128 : 64);
@@ -647,6 +689,7 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   const long ntile = (long)phases * B * p.tiles_x * p.tiles_y * p.n_tiles;
   FEMASR_CHECK_ARG(ntile < (1l << 31), "tc_igemm: too many tiles");
   p.num_tiles = (int)ntile; p.cchunks = a->Cin / 64;
+  p.gn_rows = phases * p.tiles_x * p.tiles_y * 4;
 
   CUtensorMap mah, mal, mbh, mbl;
   {

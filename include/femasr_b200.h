@@ -156,6 +156,8 @@ typedef struct {
   int act;                 /* FEMASR_ACT_* */
   void* out_hi;            /* optional: write the result as split fp16 NHWC planes (the next GEMM's operand) */
   void* out_lo;            /*           instead of fp32 y (y may then be NULL) */
+  float* gn_partial;       /* optional: GroupNorm(32) partial sums of the OUTPUT, [B][rows][32][2] fp32 with
+                              rows = femasr_tc_gn_partial_rows(H, W, upsample); finished by femasr_gn_finalize_rows */
   int upsample;            /* 1: y [B,2H,2W,Cout] = conv3x3(nearest_x2(a)), evaluated as 4 sub-pixel 2x2 convs on the
                               low-res grid; a_* are at the LOW resolution and w_blob comes from femasr_tc_pack_weight_up2 */
 } femasr_tc_args;
@@ -169,6 +171,11 @@ int femasr_tc_prepare(const float* x, void* a_hi, void* a_lo, int mode, const fl
                       const float* gamma, const float* beta, int B, int H, int W, int C, int upsample,
                       float eps, void* stream);
 int femasr_tc_igemm(const femasr_tc_args* a, void* stream);
+int femasr_tc_gn_partial_rows(int H, int W, int upsample);
+/* scale/shift tables (as femasr_gn_stats) from the partial rows a femasr_tc_igemm epilogue produced;
+ * HW = pixels per image of the tensor the partials describe. */
+int femasr_gn_finalize_rows(const float* partial, const float* gamma, const float* beta, float* scale, float* shift,
+                            int B, int rows, int HW, int C, float eps, void* stream);
 
 /* GroupNorm(32 groups, eps) statistics of NHWC x[B,HW,C] folded with the affine parameters into
  * per-(sample,channel) scale/shift: scale = rstd*gamma, shift = beta - mean*rstd*gamma

@@ -95,7 +95,8 @@ def tc_pack_up2(w_oihw):
     return blob
 
 
-def tc_igemm(hi, lo, blob, bias, Cout, ksize=3, act=0, res1=None, res2=None, y=None, upsample=0, split_out=False):
+def tc_igemm(hi, lo, blob, bias, Cout, ksize=3, act=0, res1=None, res2=None, y=None, upsample=0, split_out=False,
+             gn_partial=None):
     lib = L.load()
     B, H, W, Cin = hi.shape
     u = 2 if upsample else 1
@@ -106,6 +107,6 @@ def tc_igemm(hi, lo, blob, bias, Cout, ksize=3, act=0, res1=None, res2=None, y=N
     elif y is None:
         y = torch.empty(B, H * u, W * u, Cout, device=hi.device)
     a = L.TcArgs(p(hi), p(lo), p(blob), p(bias), p(res1), p(res2), p(y), B, H, W, Cin, Cout, ksize, act,
-                 p(oh), p(ol), upsample)
+                 p(oh), p(ol), p(gn_partial), upsample)
     L.check(lib.femasr_tc_igemm(C.byref(a), S()))
     return (oh, ol) if split_out else y

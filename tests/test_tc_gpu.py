@@ -71,6 +71,30 @@ def test_tc_upsample_conv_subpixel(cuda, B, H, W, Cin, Cout):
     assert e <= 2e-5
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,up", [(2, 24, 40, 64, 64, 0), (1, 33, 17, 128, 128, 0), (2, 16, 16, 256, 256, 0),
+                                              (1, 12, 20, 256, 128, 1), (2, 9, 72, 128, 64, 1)])
+def test_tc_epilogue_groupnorm_partials(cuda, B, H, W, Cin, Cout, up):
+    """GroupNorm statistics of the conv OUTPUT accumulated in the epilogue == a stats pass over the stored output."""
+    lib = L.load()
+    x, w, b = rnd(B, Cin, H, W, seed=27), rnd(Cout, Cin, 3, 3, seed=28, scale=0.03), rnd(Cout, seed=29)
+    u = 2 if up else 1
+    res = rnd(B, u * H, u * W, Cout, seed=30).to(cuda)
+    gamma, beta = (1 + 0.2 * rnd(Cout, seed=31)).to(cuda), (0.2 * rnd(Cout, seed=32)).to(cuda)
+    rows = lib.femasr_tc_gn_partial_rows(H, W, up)
+    part = torch.full((B, rows, 32, 2), float("nan"), device=cuda)
+    hi, lo = G.tc_prepare(G.nhwc(x).to(cuda))
+    blob = G.tc_pack_up2(w.to(cuda)) if up else G.tc_pack(w.to(cuda))
+    y = G.tc_igemm(hi, lo, blob, b.to(cuda), Cout, 3, upsample=up, res1=res, gn_partial=part)
+    assert not torch.isnan(part).any(), "every (image, row, group) partial must be written"
+    sc = torch.empty(B, Cout, device=cuda)
+    sh = torch.empty(B, Cout, device=cuda)
+    L.check(lib.femasr_gn_finalize_rows(part.data_ptr(), gamma.data_ptr(), beta.data_ptr(), sc.data_ptr(), sh.data_ptr(),
+                                        B, rows, u * H * u * W, Cout, 1e-6, G.S()))
+    sc2, sh2 = G.gn_tables(y, gamma, beta)
+    assert (sc - sc2).abs().max().item() <= 2e-6 * sc2.abs().max().item()
+    assert (sh - sh2).abs().max().item() <= 2e-6 * max(1.0, sh2.abs().max().item())
+
+
 def test_tc_split_output(cuda):
     M, K, N = 500, 256, 1024
     x, w, b = rnd(M, K, seed=24), rnd(N, K, seed=25, scale=0.05), rnd(N, seed=26)
