@@ -2,40 +2,84 @@
 //   in_conv  4x4 p1, Cin=3   NCHW -> NHWC   (femasr_arch.py:150)
 //   out_conv 3x3 p1, Cout=3  NHWC -> NCHW   (femasr_arch.py:273)
 //   weight repack, NCHW<->NHWC, flip-pad (test(), :459-460), window copy (crop / tile paste)
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace femasr {
 
-template <int KS>
+// in_conv: 4x4, pad 1, Cin = 3.  Thread = (4 output channels) x (4 consecutive output pixels of one row): the
+// 4x7x3 input patch lives in registers (loads are shared by all channel-quad threads of the pixel group through
+// L1), every weight float4 is used for 16 FMAs, and the 4 stores per thread are contiguous across the warp's
+// channel quads.  SPLIT: write the fp16 hi/lo operand planes of the following tensor-core conv instead of fp32.
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) in_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, float* __restrict__ y,
-                                                      int B, int Cin, int H, int W, int Cout) {
-  const int Ho = H + 2 - KS + 1, Wo = W + 2 - KS + 1;
+                                                      __half* __restrict__ yhi, __half* __restrict__ ylo,
+                                                      int B, int H, int W, int Cout) {
+  constexpr int KS = 4, CIN = 3, PX = 4;
+  const int Ho = H - 1, Wo = W - 1;
   const int quads = Cout / 4;
-  const int ppb = 256 / quads;                       // pixels per block
+  const int gpb = 256 / quads;                         // pixel groups per block
   const int q = threadIdx.x % quads;
-  const long pix = (long)blockIdx.x * ppb + threadIdx.x / quads;
-  const long npix = (long)B * Ho * Wo;
-  if (pix >= npix) return;
-  const int b = (int)(pix / (Ho * Wo));
-  const int r = (int)(pix - (long)b * Ho * Wo);
-  const int oy = r / Wo, ox = r - oy * Wo;
-  float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int kh = 0; kh < KS; ++kh) {
-    const int iy = oy + kh - 1;
-    if (iy < 0 || iy >= H) continue;
-    for (int kw = 0; kw < KS; ++kw) {
-      const int ix = ox + kw - 1;
-      if (ix < 0 || ix >= W) continue;
-      for (int ci = 0; ci < Cin; ++ci) {
-        const float xv = __ldg(x + (((long)b * Cin + ci) * H + iy) * W + ix);
-        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + ((long)(kh * KS + kw) * Cin + ci) * Cout) + q);
-        acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y);
-        acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
+  const int groups_x = (Wo + PX - 1) / PX;
+  const long grp = (long)blockIdx.x * gpb + threadIdx.x / quads;
+  const long ngrp = (long)B * Ho * groups_x;
+  if (grp >= ngrp) return;
+  const int gx = (int)(grp % groups_x);
+  const long t = grp / groups_x;
+  const int oy = (int)(t % Ho), b = (int)(t / Ho);
+  const int ox0 = gx * PX;
+  float patch[CIN][KS][PX + KS - 1];
+#pragma unroll
+  for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+    for (int r = 0; r < KS; ++r) {
+      const int iy = oy + r - 1;
+#pragma unroll
+      for (int cidx = 0; cidx < PX + KS - 1; ++cidx) {
+        const int ix = ox0 + cidx - 1;
+        patch[ci][r][cidx] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + (((long)b * CIN + ci) * H + iy) * W + ix) : 0.f;
       }
     }
+  float4 acc[PX];
+  const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int p = 0; p < PX; ++p) acc[p] = bv;
+#pragma unroll
+  for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < KS; ++kw)
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + ((long)(kh * KS + kw) * CIN + ci) * Cout) + q);
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          const float xv = patch[ci][kh][p + kw];
+          acc[p].x = fmaf(xv, wv.x, acc[p].x); acc[p].y = fmaf(xv, wv.y, acc[p].y);
+          acc[p].z = fmaf(xv, wv.z, acc[p].z); acc[p].w = fmaf(xv, wv.w, acc[p].w);
+        }
+      }
+#pragma unroll
+  for (int p = 0; p < PX; ++p) {
+    const int ox = ox0 + p;
+    if (ox >= Wo) break;
+    const long e = ((((long)b * Ho + oy) * Wo + ox) * Cout) + q * 4;
+    if (SPLIT) {
+      const float v[4] = {acc[p].x, acc[p].y, acc[p].z, acc[p].w};
+      __align__(8) __half h[4], l[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float cl = fminf(fmaxf(v[k], -65504.f), 65504.f);
+        h[k] = __float2half_rn(cl);
+        l[k] = __float2half_rn(cl - __half2float(h[k]));
+      }
+      *reinterpret_cast<uint2*>(yhi + e) = *reinterpret_cast<const uint2*>(h);
+      *reinterpret_cast<uint2*>(ylo + e) = *reinterpret_cast<const uint2*>(l);
+    } else {
+      *reinterpret_cast<float4*>(y + e) = acc[p];
+    }
   }
-  reinterpret_cast<float4*>(y + pix * Cout)[q] = acc;
 }
 
 // out_conv: 3x3, Cin=64 -> 3.  The input tile (with halo) is staged in shared memory by coalesced 16-byte
@@ -143,15 +187,32 @@ __global__ void copy_window_kernel(const float* __restrict__ src, float* __restr
 
 using namespace femasr;
 
+static int in_conv_launch(const float* x, const float* w, const float* bias, float* y, void* yhi, void* ylo, int B,
+                          int Cin, int H, int W, int Cout, void* stream) {
+  FEMASR_CHECK_ARG(x && w && (y || (yhi && ylo)), "in_conv: null pointer");
+  FEMASR_CHECK_ARG(B > 0 && H >= 3 && W >= 3 && Cin == 3, "in_conv: needs Cin == 3 and H, W >= 3");
+  FEMASR_CHECK_ARG(Cout % 4 == 0 && 256 % (Cout / 4) == 0 && Cout <= 1024, "in_conv: unsupported Cout");
+  const long ngrp = (long)B * (H - 1) * cdiv(W - 1, 4);
+  const int gpb = 256 / (Cout / 4);
+  const unsigned grid = (unsigned)cdiv(ngrp, gpb);
+  if (y)
+    in_conv_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(x, w, bias, y, nullptr, nullptr, B, H, W, Cout);
+  else
+    in_conv_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(x, w, bias, nullptr, reinterpret_cast<__half*>(yhi),
+                                                                reinterpret_cast<__half*>(ylo), B, H, W, Cout);
+  return launch_status("in_conv_kernel");
+}
+
 extern "C" int femasr_in_conv4x4(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int H,
                                  int W, int Cout, void* stream) {
-  FEMASR_CHECK_ARG(x && w && y, "in_conv: null pointer");
-  FEMASR_CHECK_ARG(B > 0 && H >= 3 && W >= 3 && Cin > 0, "in_conv: input too small");
-  FEMASR_CHECK_ARG(Cout % 4 == 0 && 256 % (Cout / 4) == 0 && Cout <= 1024, "in_conv: unsupported Cout");
-  const long npix = (long)B * (H - 1) * (W - 1);
-  const int ppb = 256 / (Cout / 4);
-  in_conv_kernel<4><<<(unsigned)cdiv(npix, ppb), 256, 0, as_stream(stream)>>>(x, w, bias, y, B, Cin, H, W, Cout);
-  return launch_status("in_conv_kernel");
+  FEMASR_CHECK_ARG(y, "in_conv: null output");
+  return in_conv_launch(x, w, bias, y, nullptr, nullptr, B, Cin, H, W, Cout, stream);
+}
+
+extern "C" int femasr_in_conv4x4_split(const float* x, const float* w, const float* bias, void* y_hi, void* y_lo, int B,
+                                       int Cin, int H, int W, int Cout, void* stream) {
+  FEMASR_CHECK_ARG(y_hi && y_lo, "in_conv_split: null output");
+  return in_conv_launch(x, w, bias, nullptr, y_hi, y_lo, B, Cin, H, W, Cout, stream);
 }
 
 extern "C" int femasr_out_conv3x3(const float* x, const float* w, const float* bias, float* y, int B, int H, int W,

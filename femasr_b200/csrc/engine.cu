@@ -228,7 +228,8 @@ struct Ctx {
             int stride, int upsample, int prologue, const float* pa, const float* pb, const float* gamma,
             const float* beta, int act, const float* res1, const float* res2, bool has_bias = true) {
     if (has_bias && tc_eligible(wname, Cin, Cout, ksize, stride, upsample)) {
-      conv_tc(wname, x, y, B, Hin, Win, Cin, Cout, ksize, upsample, prologue, pa, pb, gamma, beta, act, res1, res2);
+      conv_tc(wname, x, y, B, Hin, Win, Cin, Cout, ksize, upsample, prologue, pa, pb, gamma, beta, act, res1, res2,
+              nullptr, nullptr, nullptr, nullptr, nullptr, stride);
       return;
     }
     if (dry() || !ok()) return;
@@ -248,7 +249,8 @@ struct Ctx {
   }
 
   bool tc_eligible(const std::string& wname, int Cin, int Cout, int ksize, int stride, int upsample) const {
-    if (net->cfg.gemm_path != 1 || stride != 1 || (ksize != 1 && ksize != 3) || Cin % 64 || Cout % 64) return false;
+    if (net->cfg.gemm_path != 1 || (ksize != 1 && ksize != 3) || Cin % 64 || Cout % 64) return false;
+    if (stride != 1 && !(stride == 2 && ksize == 3 && !upsample)) return false;
     if (dry()) return true;
     return upsample ? net->tcw_up.count(wname + ".weight") != 0 : net->tcw.count(wname + ".weight") != 0;
   }
@@ -260,7 +262,7 @@ struct Ctx {
   void conv_tc(const std::string& wname, const float* x, float* y, int B, int Hin, int Win, int Cin, int Cout, int ksize,
                int upsample, int prologue, const float* pa, const float* pb, const float* gamma, const float* beta,
                int act, const float* res1, const float* res2, const void* pre_hi = nullptr, const void* pre_lo = nullptr,
-               void* out_hi = nullptr, void* out_lo = nullptr, float* gn_partial = nullptr) {
+               void* out_hi = nullptr, void* out_lo = nullptr, float* gn_partial = nullptr, int stride = 1) {
     const size_t plane_halves = (size_t)B * Hin * Win * Cin;
     float *ahi = nullptr, *alo = nullptr;
     if (!pre_hi) {
@@ -280,8 +282,10 @@ struct Ctx {
       t.bias = P(wname + ".bias");
       t.res1 = res1; t.res2 = res2; t.y = y; t.out_hi = out_hi; t.out_lo = out_lo; t.gn_partial = gn_partial;
       t.B = B; t.H = Hin; t.W = Win; t.Cin = Cin; t.Cout = Cout; t.ksize = ksize; t.act = act; t.upsample = upsample;
+      t.stride = stride;
       const int u = upsample ? 2 : 1;
-      const double flops = 2.0 * B * (Hin * u) * (double)(Win * u) * Cout * Cin * ksize * ksize;   // algorithmic (reference) count
+      const int Ho = stride == 2 ? (Hin - 1) / 2 + 1 : Hin * u, Wo = stride == 2 ? (Win - 1) / 2 + 1 : Win * u;
+      const double flops = 2.0 * B * Ho * (double)Wo * Cout * Cin * ksize * ksize;   // algorithmic (reference) count
       run("tc_igemm", flops, [&] { return femasr_tc_igemm(&t, st); });
     }
     if (alo) ar.release(alo);
@@ -446,22 +450,43 @@ struct Ctx {
     const std::string enc = "multiscale_encoder";
     int c = chan(256 / cfg.scale_factor);
     int h = H - 1, w = W - 1;
-    float* cur = ar.alloc((size_t)B * h * w * c);
-    {
-      const float *iw = P(enc + ".in_conv.weight"), *ib = P(enc + ".in_conv.bias");
+    const bool tc = tc_convs(c);
+    const float *iw = P(enc + ".in_conv.weight"), *ib = P(enc + ".in_conv.bias");
+    const double in_flops = 2.0 * 16 * cfg.in_channel * c * (double)B * h * w;
+    const bool want_in_tap = !dry() && net->taps.count("in_conv") && net->taps["in_conv"].dst;
+    float* cur = nullptr;                 // fp32 in_conv output (SIMT path, or when its tap is requested)
+    float* in_hi = nullptr; float* in_lo = nullptr;   // tensor-core path: in_conv writes the split operand planes directly
+    const size_t in_elems = (size_t)B * h * w * c;
+    if (!tc || want_in_tap || dry()) {
+      // (dry runs always reserve it so the workspace also covers a later tap request)
+      cur = ar.alloc(in_elems);
       const int c0 = c;
-      run("in_conv", 2.0 * 16 * cfg.in_channel * c0 * (double)B * h * w,
-          [&] { return femasr_in_conv4x4(x_nchw, iw, ib, cur, B, cfg.in_channel, H, W, c0, st); });
+      if (!tc || want_in_tap)
+        run("in_conv", in_flops, [&] { return femasr_in_conv4x4(x_nchw, iw, ib, cur, B, cfg.in_channel, H, W, c0, st); });
+      tap("in_conv", cur, in_elems);
     }
-    tap("in_conv", cur, (size_t)B * h * w * c);
+    if (tc) {
+      in_hi = ar.alloc((in_elems + 1) / 2);
+      in_lo = ar.alloc((in_elems + 1) / 2);
+      const int c0 = c;
+      run("in_conv", in_flops, [&] { return femasr_in_conv4x4_split(x_nchw, iw, ib, in_hi, in_lo, B, cfg.in_channel, H, W, c0, st); });
+    }
     for (int i = 0; i < d; ++i) {
       const std::string b = enc + ".blocks." + std::to_string(i);
       const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1, co = 256;
       float* nxt = ar.alloc((size_t)B * ho * wo * co);
-      conv(b + ".0", cur, nxt, B, h, w, c, co, 3, 2, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
-      ar.release(cur);
+      Stats sd0;
+      if (tc) {
+        sd0 = alloc_stats(B, ho, wo, 0);
+        conv_tc(b + ".0", cur, nxt, B, h, w, c, co, 3, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
+                i == 0 ? in_hi : nullptr, i == 0 ? in_lo : nullptr, nullptr, nullptr, sd0.partial, 2);
+      } else {
+        conv(b + ".0", cur, nxt, B, h, w, c, co, 3, 2, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
+      }
+      if (i == 0 && in_lo) { ar.release(in_lo); ar.release(in_hi); in_lo = in_hi = nullptr; }
+      if (cur) ar.release(cur);
       cur = nxt; h = ho; w = wo; c = co;
-      Stats sd = resblock(b + ".1", cur, B, h, w, c, nullptr, Stats(), true);
+      Stats sd = resblock(b + ".1", cur, B, h, w, c, nullptr, sd0, true);
       resblock(b + ".2", cur, B, h, w, c, nullptr, sd, false);
     }
     tap("down", cur, (size_t)B * h * w * c);

@@ -71,28 +71,38 @@ __global__ void gn_finalize_kernel(const double* __restrict__ partial, const flo
 }
 
 // Same, from the fp32 partial rows the tensor-core conv epilogue wrote: partial[b][row][g][2].
-__global__ void gn_finalize_rows_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
-                                        const float* __restrict__ beta, float* __restrict__ scale,
-                                        float* __restrict__ shift, int HW, int C, int rows, float eps) {
-  const int b = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// One CTA per image: lane = group (coalesced 256-byte row reads), 32 row slices reduced through shared memory
+// in a fixed order.
+__global__ void __launch_bounds__(1024) gn_finalize_rows_kernel(const float* __restrict__ partial,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float* __restrict__ scale,
+                                                                float* __restrict__ shift, int HW, int C, int rows, float eps) {
+  __shared__ double red[2][32][33];
+  const int b = blockIdx.x, g = threadIdx.x & 31, slice = threadIdx.x >> 5;
   double a = 0.0, a2 = 0.0;
-  for (int r = lane; r < rows; r += 32) {
-    const float2 v = *reinterpret_cast<const float2*>(partial + (((long)b * rows + r) * GN_GROUPS + g) * 2);
+  const float2* base = reinterpret_cast<const float2*>(partial) + (long)b * rows * GN_GROUPS + g;
+  for (int r = slice; r < rows; r += 32) {
+    const float2 v = __ldg(base + (long)r * GN_GROUPS);
     a += (double)v.x; a2 += (double)v.y;
   }
-  a = warp_sum_d(a); a2 = warp_sum_d(a2);
-  const int cpg = C / GN_GROUPS;
-  const double n = (double)HW * cpg;
-  const double mean = a / n;
-  double var = a2 / n - mean * mean;
-  if (var < 0.0) var = 0.0;
-  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-  const float meanf = (float)mean;
-  if (lane < cpg) {
-    const int c = g * cpg + lane;
-    const float sc = rstd * gamma[c];
-    scale[(long)b * C + c] = sc;
-    shift[(long)b * C + c] = fmaf(-sc, meanf, beta[c]);
+  red[0][slice][g] = a; red[1][slice][g] = a2;
+  __syncthreads();
+  if (slice == 0) {
+    a = 0.0; a2 = 0.0;
+    for (int s = 0; s < 32; ++s) { a += red[0][s][g]; a2 += red[1][s][g]; }
+    const int cpg = C / GN_GROUPS;
+    const double n = (double)HW * cpg;
+    const double mean = a / n;
+    double var = a2 / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float meanf = (float)mean;
+    for (int k = 0; k < cpg; ++k) {
+      const int c = g * cpg + k;
+      const float sc = rstd * gamma[c];
+      scale[(long)b * C + c] = sc;
+      shift[(long)b * C + c] = fmaf(-sc, meanf, beta[c]);
+    }
   }
 }
 

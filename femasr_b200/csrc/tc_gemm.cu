@@ -118,6 +118,7 @@ struct TcP {
   float* gn_partial;                // when set: per-(image, tile, lane-quarter) GroupNorm partial sums of the OUTPUT
   int gn_rows, cpg;                 // partial rows per image; channels per group (Cout / 32)
   int B, H, W, Cin, Cout, taps, act;
+  int stride;                    // 1 or 2 (3x3 stride-2: TMA traversal stride 2, tiles run over the output grid)
   int up;                        // 1: nearest-x2 upsample + 3x3 conv evaluated as 4 sub-pixel phases of 2x2 taps
   int Wt, Ht, wt_shift;          // 128-pixel tile = Ht rows x Wt cols (Wt power of two)
   int tiles_x, tiles_y, n_tiles; // per image spatial tiles, Cout / BN
@@ -193,8 +194,8 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
         mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-        tma_load_4d(sa, &map_a_hi, full_bar(stage), c0, x0 + dx, y0 + dy, b);
-        tma_load_4d(sa + A_PLANE_BYTES, &map_a_lo, full_bar(stage), c0, x0 + dx, y0 + dy, b);
+        tma_load_4d(sa, &map_a_hi, full_bar(stage), c0, p.stride * x0 + dx, p.stride * y0 + dy, b);
+        tma_load_4d(sa + A_PLANE_BYTES, &map_a_lo, full_bar(stage), c0, p.stride * x0 + dx, p.stride * y0 + dy, b);
         tma_load_2d(sa + 2 * A_PLANE_BYTES, &map_b_hi, full_bar(stage), tap * p.Cin + c0, n0);
         tma_load_2d(sa + 2 * A_PLANE_BYTES + BN * TC_BK * 2, &map_b_lo, full_bar(stage), tap * p.Cin + c0, n0);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -301,7 +302,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c + 4 * j));
             o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
           }
-          if (p.act == FEMASR_ACT_GELU) { o.x = gelu_erf_f(o.x); o.y = gelu_erf_f(o.y); o.z = gelu_erf_f(o.z); o.w = gelu_erf_f(o.w); }
+          if (p.act == FEMASR_ACT_GELU) { o.x = gelu_erf_fast_f(o.x); o.y = gelu_erf_fast_f(o.y); o.z = gelu_erf_fast_f(o.z); o.w = gelu_erf_fast_f(o.w); }
           *reinterpret_cast<float4*>(&stage[lane * 16 + 4 * (j ^ ((lane >> 1) & 3))]) = o;
         }
         __syncwarp();
@@ -532,10 +533,11 @@ static EncodeTiledFn get_encode() {
 }
 
 static int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                    const cuuint32_t* box) {
+                    const cuuint32_t* box, int spatial_stride = 1) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(FEMASR_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1};
+  if (rank == 2) estr[1] = 1;
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -662,7 +664,12 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   FEMASR_CHECK_ARG(!a->upsample || a->ksize == 3, "tc_igemm: upsample fusion needs ksize 3 (and an up2 weight blob)");
   FEMASR_CHECK_ARG(a->Cin % 64 == 0 && a->Cout % 64 == 0, "tc_igemm: Cin and Cout must be multiples of 64");
   int B = a->B, H = a->H, W = a->W;
+  const int stride = a->stride == 2 ? 2 : 1;
+  FEMASR_CHECK_ARG(a->stride >= 0 && a->stride <= 2, "tc_igemm: stride must be 1 or 2");
+  FEMASR_CHECK_ARG(stride == 1 || (a->ksize == 3 && !a->upsample), "tc_igemm: stride 2 needs a plain 3x3 conv");
   if (a->ksize == 1) { W = B * H * W; H = 1; B = 1; }     // pointwise: one long row of tokens
+  const int Hin = H, Win = W;                             // activation-plane dims
+  if (stride == 2) { H = (H - 1) / 2 + 1; W = (W - 1) / 2 + 1; }   // tiles run over the output grid
   FEMASR_CHECK_ARG((long)W < (1l << 31), "tc_igemm: too many rows");
   const int taps = a->upsample ? 4 : a->ksize * a->ksize;
   const int phases = a->upsample ? 4 : 1;
@@ -679,7 +686,7 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   FEMASR_CHECK_ARG(!a->gn_partial || (a->ksize == 3 && (a->Cout == 64 || a->Cout == 128 || a->Cout == 256)),
                    "tc_igemm: gn_partial needs a 3x3 conv with Cout in {64,128,256}");
   p.B = B; p.H = H; p.W = W; p.Cin = a->Cin; p.Cout = a->Cout; p.taps = taps; p.act = a->act;
-  p.up = a->upsample ? 1 : 0;
+  p.up = a->upsample ? 1 : 0; p.stride = stride;
   // tile shape: the widest power-of-two Wt <= 128 that wastes the fewest padded pixels
   tc_tile_shape(H, W, &p.Wt, &p.Ht);
   p.wt_shift = 0; while ((1 << p.wt_shift) < p.Wt) ++p.wt_shift;
@@ -693,12 +700,13 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
 
   CUtensorMap mah, mal, mbh, mbl;
   {
-    const cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    const cuuint64_t str[3] = {(cuuint64_t)a->Cin * 2, (cuuint64_t)W * a->Cin * 2, (cuuint64_t)H * W * a->Cin * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)p.Wt, (cuuint32_t)p.Ht, 1};
-    int s = make_map(&mah, a->a_hi, 4, dims, str, box);
+    const cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
+    const cuuint64_t str[3] = {(cuuint64_t)a->Cin * 2, (cuuint64_t)Win * a->Cin * 2, (cuuint64_t)Hin * Win * a->Cin * 2};
+    // with a traversal stride s the box spans s*Wt x s*Ht source pixels and lands Wt x Ht of them in smem
+    const cuuint32_t box[4] = {64, (cuuint32_t)(p.Wt * stride), (cuuint32_t)(p.Ht * stride), 1};
+    int s = make_map(&mah, a->a_hi, 4, dims, str, box, stride);
     if (s) return s;
-    s = make_map(&mal, a->a_lo, 4, dims, str, box);
+    s = make_map(&mal, a->a_lo, 4, dims, str, box, stride);
     if (s) return s;
   }
   {

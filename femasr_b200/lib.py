@@ -45,7 +45,7 @@ class TcArgs(C.Structure):
                 ("res1", C.c_void_p), ("res2", C.c_void_p), ("y", C.c_void_p),
                 ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
                 ("ksize", C.c_int), ("act", C.c_int), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
-                ("gn_partial", C.c_void_p), ("upsample", C.c_int)]
+                ("stride", C.c_int), ("gn_partial", C.c_void_p), ("upsample", C.c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/femasr_b200.h declares
@@ -89,6 +89,7 @@ SIGNATURES = {
     "femasr_sum_scaled": (_I, [_V, _V, _Z, _D, _V]),
     "femasr_codebook_gather": (_I, [_V, _V, _V, _I, _I, _I, _V]),
     "femasr_in_conv4x4": (_I, [_V, _V, _V, _V, _I, _I, _I, _I, _I, _V]),
+    "femasr_in_conv4x4_split": (_I, [_V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _V]),
     "femasr_out_conv3x3": (_I, [_V, _V, _V, _V, _I, _I, _I, _I, _V]),
     "femasr_nchw_to_nhwc": (_I, [_V, _V, _I, _I, _I, _I, _V]),
     "femasr_nhwc_to_nchw": (_I, [_V, _V, _I, _I, _I, _I, _V]),

@@ -156,8 +156,11 @@ typedef struct {
   int act;                 /* FEMASR_ACT_* */
   void* out_hi;            /* optional: write the result as split fp16 NHWC planes (the next GEMM's operand) */
   void* out_lo;            /*           instead of fp32 y (y may then be NULL) */
+  int stride;              /* 0|1: stride 1.  2: 3x3 stride-2 conv (pad 1); H,W are the INPUT dims, y is
+                              [B,(H-1)/2+1,(W-1)/2+1,Cout] (TMA traversal stride 2 on the activation planes) */
   float* gn_partial;       /* optional: GroupNorm(32) partial sums of the OUTPUT, [B][rows][32][2] fp32 with
-                              rows = femasr_tc_gn_partial_rows(H, W, upsample); finished by femasr_gn_finalize_rows */
+                              rows = femasr_tc_gn_partial_rows(Ht, Wt, upsample) where (Ht,Wt) is the grid the tiles run
+                              over (= H,W; the OUTPUT dims for stride 2); finished by femasr_gn_finalize_rows */
   int upsample;            /* 1: y [B,2H,2W,Cout] = conv3x3(nearest_x2(a)), evaluated as 4 sub-pixel 2x2 convs on the
                               low-res grid; a_* are at the LOW resolution and w_blob comes from femasr_tc_pack_weight_up2 */
 } femasr_tc_args;
@@ -216,6 +219,9 @@ int femasr_codebook_gather(const int64_t* idx, const float* codebook, float* zq,
  * w packed [16*Cin][Cout]. */
 int femasr_in_conv4x4(const float* x_nchw, const float* w, const float* bias, float* y_nhwc, int B,
                       int Cin, int H, int W, int Cout, void* stream);
+/* same, but the result is written as the split fp16 operand planes of the following tensor-core conv */
+int femasr_in_conv4x4_split(const float* x_nchw, const float* w, const float* bias, void* y_hi, void* y_lo, int B,
+                            int Cin, int H, int W, int Cout, void* stream);
 /* out_conv (femasr_arch.py:273): 3x3 pad 1, NHWC [B,H,W,Cin] -> NCHW [B,3,H,W].  w packed [9*Cin][3]. */
 int femasr_out_conv3x3(const float* x_nhwc, const float* w, const float* bias, float* y_nchw, int B,
                        int H, int W, int Cin, void* stream);

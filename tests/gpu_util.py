@@ -96,17 +96,18 @@ def tc_pack_up2(w_oihw):
 
 
 def tc_igemm(hi, lo, blob, bias, Cout, ksize=3, act=0, res1=None, res2=None, y=None, upsample=0, split_out=False,
-             gn_partial=None):
+             gn_partial=None, stride=1):
     lib = L.load()
     B, H, W, Cin = hi.shape
     u = 2 if upsample else 1
+    Ho, Wo = ((H - 1) // 2 + 1, (W - 1) // 2 + 1) if stride == 2 else (H * u, W * u)
     oh = ol = None
     if split_out:
-        oh = torch.empty(B, H * u, W * u, Cout, dtype=torch.float16, device=hi.device)
+        oh = torch.empty(B, Ho, Wo, Cout, dtype=torch.float16, device=hi.device)
         ol = torch.empty_like(oh)
     elif y is None:
-        y = torch.empty(B, H * u, W * u, Cout, device=hi.device)
+        y = torch.empty(B, Ho, Wo, Cout, device=hi.device)
     a = L.TcArgs(p(hi), p(lo), p(blob), p(bias), p(res1), p(res2), p(y), B, H, W, Cin, Cout, ksize, act,
-                 p(oh), p(ol), p(gn_partial), upsample)
+                 p(oh), p(ol), stride, p(gn_partial), upsample)
     L.check(lib.femasr_tc_igemm(C.byref(a), S()))
     return (oh, ol) if split_out else y

@@ -95,6 +95,33 @@ def test_tc_epilogue_groupnorm_partials(cuda, B, H, W, Cin, Cout, up):
     assert (sh - sh2).abs().max().item() <= 2e-6 * max(1.0, sh2.abs().max().item())
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 31, 31, 256, 256), (1, 63, 47, 128, 256), (1, 16, 24, 256, 256)])
+def test_tc_stride2_conv(cuda, B, H, W, Cin, Cout):
+    """3x3 stride-2 pad-1 conv through TMA traversal strides (femasr_arch.py:159)."""
+    x, w, b = rnd(B, Cin, H, W, seed=33), rnd(Cout, Cin, 3, 3, seed=34, scale=0.03), rnd(Cout, seed=35)
+    want = F.conv2d(x.double(), w.double(), b.double(), stride=2, padding=1)
+    hi, lo = G.tc_prepare(G.nhwc(x).to(cuda))
+    y = G.tc_igemm(hi, lo, G.tc_pack(w.to(cuda)), b.to(cuda), Cout, 3, stride=2)
+    assert tuple(G.nchw(y).shape) == tuple(want.shape)
+    e = rel_err(G.nchw(y), want)
+    print(f"tc stride-2 conv {B}x{H}x{W} {Cin}->{Cout}: rel err {e:.2e}")
+    assert e <= 2e-5
+
+
+def test_in_conv_split_planes(cuda):
+    lib = L.load()
+    B, H, W, cout = 2, 18, 23, 256
+    x, w, b = torch.rand(B, 3, H, W), rnd(cout, 3, 4, 4, seed=36, scale=0.15), rnd(cout, seed=37)
+    want = F.conv2d(x, w, b, padding=1)
+    hi = torch.empty(B, H - 1, W - 1, cout, dtype=torch.float16, device=cuda)
+    lo = torch.empty_like(hi)
+    xg, wp, bg = x.to(cuda), G.pack_weight(w.to(cuda)), b.to(cuda)
+    L.check(lib.femasr_in_conv4x4_split(xg.data_ptr(), wp.data_ptr(), bg.data_ptr(), hi.data_ptr(), lo.data_ptr(),
+                                        B, 3, H, W, cout, G.S()))
+    got = (hi.float() + lo.float()).permute(0, 3, 1, 2).cpu()
+    assert (got - want).abs().max().item() <= 5e-6
+
+
 def test_tc_split_output(cuda):
     M, K, N = 500, 256, 1024
     x, w, b = rnd(M, K, seed=24), rnd(N, K, seed=25, scale=0.05), rnd(N, seed=26)
