@@ -98,6 +98,7 @@ struct femasr_net {
   std::map<std::string, Tap> taps;
   int last_launches = 0;
   bool profile = false;
+  bool tc_precise = true;                 // K-sliced fp32 accumulation for the layers in front of the VQ
   std::vector<ProfRec> prof;
   std::string prof_json;
   ~femasr_net() {
@@ -182,6 +183,7 @@ struct Ctx {
   Arena ar;
   cudaStream_t st;
   int status = FEMASR_OK;
+  bool precise_region = false;   // true while emitting the layers in front of the VQ (index-critical)
   bool dry() const { return ar.dry; }
   bool ok() const { return status == FEMASR_OK; }
   void check(int s) { if (status == FEMASR_OK && s != FEMASR_OK) status = s; }
@@ -262,7 +264,8 @@ struct Ctx {
   void conv_tc(const std::string& wname, const float* x, float* y, int B, int Hin, int Win, int Cin, int Cout, int ksize,
                int upsample, int prologue, const float* pa, const float* pb, const float* gamma, const float* beta,
                int act, const float* res1, const float* res2, const void* pre_hi = nullptr, const void* pre_lo = nullptr,
-               void* out_hi = nullptr, void* out_lo = nullptr, float* gn_partial = nullptr, int stride = 1) {
+               void* out_hi = nullptr, void* out_lo = nullptr, float* gn_partial = nullptr, int stride = 1,
+               bool precise = false) {
     const size_t plane_halves = (size_t)B * Hin * Win * Cin;
     float *ahi = nullptr, *alo = nullptr;
     if (!pre_hi) {
@@ -286,7 +289,26 @@ struct Ctx {
       const int u = upsample ? 2 : 1;
       const int Ho = stride == 2 ? (Hin - 1) / 2 + 1 : Hin * u, Wo = stride == 2 ? (Win - 1) / 2 + 1 : Win * u;
       const double flops = 2.0 * B * Ho * (double)Wo * Cout * Cin * ksize * ksize;   // algorithmic (reference) count
-      run("tc_igemm", flops, [&] { return femasr_tc_igemm(&t, st); });
+      const int nkb = (upsample ? 4 : ksize * ksize) * (Cin / 64);
+      const int slice = 4;                       // 4 k-blocks = 256 of K per launch
+      if ((precise || precise_region) && net->tc_precise && nkb > slice && y && !out_hi && act == 0) {
+        // K-sliced accumulation (layers in front of the VQ): each launch adds one 256-deep slice to y in fp32
+        // round-to-nearest (res1 = y), so the tensor core's truncating accumulator never runs longer than a slice.
+        for (int k0 = 0; k0 < nkb; k0 += slice) {
+          femasr_tc_args ts = t;
+          ts.kb_begin = k0; ts.kb_count = std::min(slice, nkb - k0);
+          const bool first = k0 == 0, last = k0 + slice >= nkb;
+          ts.bias = first ? t.bias : nullptr;
+          ts.res1 = first ? t.res1 : y;
+          ts.res2 = first ? t.res2 : nullptr;
+          ts.gn_partial = last ? t.gn_partial : nullptr;
+          ts.act = 0;
+          const double f = flops * ts.kb_count / nkb;
+          run("tc_igemm", f, [&] { return femasr_tc_igemm(&ts, st); });
+        }
+      } else {
+        run("tc_igemm", flops, [&] { return femasr_tc_igemm(&t, st); });
+      }
     }
     if (alo) ar.release(alo);
     if (ahi) ar.release(ahi);
@@ -451,6 +473,7 @@ struct Ctx {
     int c = chan(256 / cfg.scale_factor);
     int h = H - 1, w = W - 1;
     const bool tc = tc_convs(c);
+    precise_region = true;
     const float *iw = P(enc + ".in_conv.weight"), *ib = P(enc + ".in_conv.bias");
     const double in_flops = 2.0 * 16 * cfg.in_channel * c * (double)B * h * w;
     const bool want_in_tap = !dry() && net->taps.count("in_conv") && net->taps["in_conv"].dst;
@@ -493,6 +516,7 @@ struct Ctx {
     swin(enc + ".blocks." + std::to_string(d), cur, B, h, w);
     tap("swin", cur, (size_t)B * h * w * c);
     float *u1 = nullptr, *u2 = nullptr;
+    precise_region = false;        // the up branches only reach the decoder's skip adds (femasr_arch.py:313-314)
     if (cfg.use_residual) {
       const std::string b1 = enc + ".blocks." + std::to_string(d + 1), b2 = enc + ".blocks." + std::to_string(d + 2);
       u1 = up_block(b1 + ".1", b1 + ".2", b1 + ".3", cur, B, h, w, 256, 256, nullptr);
@@ -501,6 +525,7 @@ struct Ctx {
       tap("up2", u2, (size_t)B * 4 * h * 4 * w * 128);
     }
     // feature matching
+    precise_region = true;
     const size_t N = (size_t)B * h * w;
     float* z = ar.alloc(N * e);
     conv("before_quant_group.0", cur, z, B, h, w, 256, e, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
@@ -518,6 +543,7 @@ struct Ctx {
     ar.release(lrows);
     ar.release(zc);
     tap("zq", zq, N * e);
+    precise_region = false;
     decode(cfg.use_quantize ? zq : z, y_nchw, B, h, w, u1, u2);
     if (u2) ar.release(u2);
     if (u1) ar.release(u1);
@@ -572,6 +598,7 @@ extern "C" int femasr_net_create(const femasr_net_config* cfg, femasr_net** out)
   femasr_net* n = new femasr_net();
   n->cfg = *cfg;
   n->depth = cfg->scale_factor == 4 ? 1 : 2;
+  if (const char* ev = getenv("FEMASR_TC_PRECISE")) n->tc_precise = atoi(ev) != 0;
   build_spec(n);
   *out = n;
   return FEMASR_OK;

@@ -123,6 +123,7 @@ struct TcP {
   int Wt, Ht, wt_shift;          // 128-pixel tile = Ht rows x Wt cols (Wt power of two)
   int tiles_x, tiles_y, n_tiles; // per image spatial tiles, Cout / BN
   int num_tiles, cchunks;        // total tiles, Cin / 64
+  int kb_begin, kb_end;          // k-block range of this launch (a K-slice; the caller sums slices through res1)
 };
 
 constexpr int TC_BM = 128, TC_BK = 64;
@@ -185,7 +186,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       const int ph = mt / p.B;                       // sub-pixel phase (0 unless p.up)
       const int py = ph >> 1, px = ph & 1;
       const int x0 = tx * p.Wt, y0 = ty * p.Ht, n0 = ph * p.Cout + nt * BN;
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
         const int tap = kb / p.cchunks;
         const int c0 = (kb - tap * p.cchunks) * TC_BK;
         int dy = 0, dx = 0;
@@ -212,7 +213,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -223,7 +224,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         for (int k = 0; k < TC_BK / 16; ++k) {
           const uint64_t ko = (uint64_t)((k * 32) >> 4);   // +32 bytes per k-step inside the 128B swizzle atom
           // small cross terms first, the dominant hi*hi product last
-          umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, (kb != p.kb_begin || k != 0) ? 1u : 0u);
           umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
           umma_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
         }
@@ -696,6 +697,9 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   const long ntile = (long)phases * B * p.tiles_x * p.tiles_y * p.n_tiles;
   FEMASR_CHECK_ARG(ntile < (1l << 31), "tc_igemm: too many tiles");
   p.num_tiles = (int)ntile; p.cchunks = a->Cin / 64;
+  const int nkb_total = taps * p.cchunks;
+  p.kb_begin = a->kb_begin; p.kb_end = a->kb_count > 0 ? a->kb_begin + a->kb_count : nkb_total;
+  FEMASR_CHECK_ARG(p.kb_begin >= 0 && p.kb_begin < p.kb_end && p.kb_end <= nkb_total, "tc_igemm: bad k-block slice");
   p.gn_rows = phases * p.tiles_x * p.tiles_y * 4;
 
   CUtensorMap mah, mal, mbh, mbl;

@@ -158,6 +158,9 @@ typedef struct {
   void* out_lo;            /*           instead of fp32 y (y may then be NULL) */
   int stride;              /* 0|1: stride 1.  2: 3x3 stride-2 conv (pad 1); H,W are the INPUT dims, y is
                               [B,(H-1)/2+1,(W-1)/2+1,Cout] (TMA traversal stride 2 on the activation planes) */
+  int kb_begin, kb_count;  /* K-slice in 64-wide k-blocks (k = tap*Cin + c); kb_count 0 = everything.  Slices are summed
+                              by the caller in fp32 (round-to-nearest) by chaining launches with res1 = y, which bounds
+                              the tensor-core accumulator's truncation error to one slice */
   float* gn_partial;       /* optional: GroupNorm(32) partial sums of the OUTPUT, [B][rows][32][2] fp32 with
                               rows = femasr_tc_gn_partial_rows(Ht, Wt, upsample) where (Ht,Wt) is the grid the tiles run
                               over (= H,W; the OUTPUT dims for stride 2); finished by femasr_gn_finalize_rows */

@@ -108,6 +108,24 @@ def test_tc_stride2_conv(cuda, B, H, W, Cin, Cout):
     assert e <= 2e-5
 
 
+def test_tc_k_sliced_accumulation(cuda):
+    """Summing 256-deep K slices in fp32 (chained launches, res1 = y) bounds the accumulator truncation."""
+    B, H, W, Cin, Cout = 1, 24, 40, 256, 256
+    x, w, b = rnd(B, Cin, H, W, seed=38), rnd(Cout, Cin, 3, 3, seed=39, scale=0.03), rnd(Cout, seed=40)
+    res = rnd(B, H, W, Cout, seed=41).to(cuda)
+    want = F.conv2d(x.double(), w.double(), b.double(), padding=1) + res.cpu().permute(0, 3, 1, 2).double()
+    hi, lo = G.tc_prepare(G.nhwc(x).to(cuda))
+    blob, bg = G.tc_pack(w.to(cuda)), b.to(cuda)
+    one = G.tc_igemm(hi, lo, blob, bg, Cout, 3, res1=res)
+    y = torch.empty(B, H, W, Cout, device=cuda)
+    nkb = 9 * Cin // 64
+    for k0 in range(0, nkb, 4):
+        G.tc_igemm(hi, lo, blob, bg if k0 == 0 else None, Cout, 3, res1=res if k0 == 0 else y, y=y, kb_begin=k0, kb_count=4)
+    e1, e2 = rel_err(G.nchw(one), want), rel_err(G.nchw(y), want)
+    print(f"K=2304 conv: single pass rel err {e1:.2e}, K-sliced {e2:.2e}")
+    assert e2 <= 2e-6 and e2 < e1
+
+
 def test_in_conv_split_planes(cuda):
     lib = L.load()
     B, H, W, cout = 2, 18, 23, 256
