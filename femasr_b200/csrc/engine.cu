@@ -291,24 +291,12 @@ struct Ctx {
       const double flops = 2.0 * B * Ho * (double)Wo * Cout * Cin * ksize * ksize;   // algorithmic (reference) count
       const int nkb = (upsample ? 4 : ksize * ksize) * (Cin / 64);
       const int slice = 4;                       // 4 k-blocks = 256 of K per launch
-      if ((precise || precise_region) && net->tc_precise && nkb > slice && y && !out_hi && act == 0) {
-        // K-sliced accumulation (layers in front of the VQ): each launch adds one 256-deep slice to y in fp32
-        // round-to-nearest (res1 = y), so the tensor core's truncating accumulator never runs longer than a slice.
-        for (int k0 = 0; k0 < nkb; k0 += slice) {
-          femasr_tc_args ts = t;
-          ts.kb_begin = k0; ts.kb_count = std::min(slice, nkb - k0);
-          const bool first = k0 == 0, last = k0 + slice >= nkb;
-          ts.bias = first ? t.bias : nullptr;
-          ts.res1 = first ? t.res1 : y;
-          ts.res2 = first ? t.res2 : nullptr;
-          ts.gn_partial = last ? t.gn_partial : nullptr;
-          ts.act = 0;
-          const double f = flops * ts.kb_count / nkb;
-          run("tc_igemm", f, [&] { return femasr_tc_igemm(&ts, st); });
-        }
-      } else {
-        run("tc_igemm", flops, [&] { return femasr_tc_igemm(&t, st); });
+      if ((precise || precise_region) && net->tc_precise && nkb > slice) {
+        // K-sliced accumulation (layers in front of the VQ): every 256 of K the tensor core's truncating accumulator
+        // is folded into an fp32 round-to-nearest running sum held in TMEM (see femasr_tc_args.slice_kb)
+        t.slice_kb = slice;
       }
+      run("tc_igemm", flops, [&] { return femasr_tc_igemm(&t, st); });
     }
     if (alo) ar.release(alo);
     if (ahi) ar.release(ahi);

@@ -100,6 +100,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // K-major, 128B-swizzled operand tile ([rows][64 fp16], 8-row atoms of 1024 B): SBO = 1024 B, LBO unused (=1),
 // descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  cute::UMMA::SmemDescriptor bit layout.
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
@@ -124,6 +140,9 @@ struct TcP {
   int tiles_x, tiles_y, n_tiles; // per image spatial tiles, Cout / BN
   int num_tiles, cchunks;        // total tiles, Cin / 64
   int kb_begin, kb_end;          // k-block range of this launch (a K-slice; the caller sums slices through res1)
+  int slice_kb;                  // >0: in-kernel K slicing - every slice_kb k-blocks the accumulator is drained into an
+                                 // fp32 running sum kept in the second TMEM buffer (round-to-nearest adds by the
+                                 // epilogue warps), so the truncating MMA accumulator never runs longer than a slice
 };
 
 constexpr int TC_BM = 128, TC_BK = 64;
@@ -209,30 +228,37 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
+    const bool sliced = p.slice_kb > 0;
+    const int slice_len = sliced ? p.slice_kb : (p.kb_end - p.kb_begin);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+      for (int kb0 = p.kb_begin; kb0 < p.kb_end; kb0 += slice_len) {
+        const int kb1 = min(kb0 + slice_len, p.kb_end);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-        const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + A_PLANE_BYTES);
-        const uint64_t b_hi = make_sw128_desc(sa + 2 * A_PLANE_BYTES);
-        const uint64_t b_lo = make_sw128_desc(sa + 2 * A_PLANE_BYTES + BN * TC_BK * 2);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + A_PLANE_BYTES);
+          const uint64_t b_hi = make_sw128_desc(sa + 2 * A_PLANE_BYTES);
+          const uint64_t b_lo = make_sw128_desc(sa + 2 * A_PLANE_BYTES + BN * TC_BK * 2);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint64_t ko = (uint64_t)((k * 32) >> 4);   // +32 bytes per k-step inside the 128B swizzle atom
-          // small cross terms first, the dominant hi*hi product last
-          umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, (kb != p.kb_begin || k != 0) ? 1u : 0u);
-          umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-          umma_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t ko = (uint64_t)((k * 32) >> 4);   // +32 bytes per k-step inside the 128B swizzle atom
+            // small cross terms first, the dominant hi*hi product last
+            umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+            umma_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+          }
+          umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        umma_commit(tfull_bar(acc));              // (partial) accumulator complete -> epilogue
+        // sliced: one MMA target buffer (0), the other holds the running sum; else ping-pong the two accumulators
+        if (sliced) acc_phase ^= 1u;
+        else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
-      umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
@@ -253,6 +279,8 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const int q = lane & 3, rsub = lane >> 2;
     constexpr int CH = 16, NCH = BN / 2 / CH;       // chunks per warp
     int acc = 0; uint32_t acc_phase = 0;
+    const bool sliced = p.slice_kb > 0;
+    const int nslices = sliced ? (p.kb_end - p.kb_begin + p.slice_kb - 1) / p.slice_kb : 1;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       int mt = tile / p.n_tiles;
@@ -276,6 +304,29 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         for (int it = 0; it < 4; ++it)
           cur[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.res1 + offs[it]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      // sliced accumulation: fold all but the last partial into the running sum S (second TMEM buffer)
+      const uint32_t t_sum = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(BN + half * (BN / 2));
+      for (int s = 0; s + 1 < nslices; ++s) {
+        mbar_wait(tfull_bar(0), acc_phase);
+        acc_phase ^= 1u;
+        tc_fence_after();
+        const uint32_t t_part = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(half * (BN / 2));
+#pragma unroll 1
+        for (int ci = 0; ci < NCH; ++ci) {
+          uint32_t pr[16];
+          tmem_ld16(t_part + (uint32_t)(ci * CH), pr);
+          if (s > 0) {
+            uint32_t sr[16];
+            tmem_ld16(t_sum + (uint32_t)(ci * CH), sr);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pr[j] = __float_as_uint(__uint_as_float(pr[j]) + __uint_as_float(sr[j]));
+          }
+          tmem_st16(t_sum + (uint32_t)(ci * CH), pr);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(tempty_bar(0));
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
@@ -294,6 +345,12 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
             : "r"(t_row + (uint32_t)c) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (nslices > 1) {
+          uint32_t sr[16];
+          tmem_ld16(t_sum + (uint32_t)c, sr);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(sr[j]));
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float4 o;
@@ -366,7 +423,8 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));             // 256 arrivals release the accumulator
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (sliced) acc_phase ^= 1u;
+      else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
   tc_fence_before();
@@ -700,6 +758,8 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   const int nkb_total = taps * p.cchunks;
   p.kb_begin = a->kb_begin; p.kb_end = a->kb_count > 0 ? a->kb_begin + a->kb_count : nkb_total;
   FEMASR_CHECK_ARG(p.kb_begin >= 0 && p.kb_begin < p.kb_end && p.kb_end <= nkb_total, "tc_igemm: bad k-block slice");
+  FEMASR_CHECK_ARG(a->slice_kb >= 0, "tc_igemm: slice_kb must be >= 0");
+  p.slice_kb = (a->slice_kb > 0 && a->slice_kb < p.kb_end - p.kb_begin) ? a->slice_kb : 0;
   p.gn_rows = phases * p.tiles_x * p.tiles_y * 4;
 
   CUtensorMap mah, mal, mbh, mbl;

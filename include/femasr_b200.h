@@ -161,6 +161,8 @@ typedef struct {
   int kb_begin, kb_count;  /* K-slice in 64-wide k-blocks (k = tap*Cin + c); kb_count 0 = everything.  Slices are summed
                               by the caller in fp32 (round-to-nearest) by chaining launches with res1 = y, which bounds
                               the tensor-core accumulator's truncation error to one slice */
+  int slice_kb;            /* >0: the same slicing inside ONE launch - every slice_kb k-blocks the MMA accumulator is
+                              drained into an fp32 running sum held in the second TMEM buffer (tcgen05.ld/st, RN adds) */
   float* gn_partial;       /* optional: GroupNorm(32) partial sums of the OUTPUT, [B][rows][32][2] fp32 with
                               rows = femasr_tc_gn_partial_rows(Ht, Wt, upsample) where (Ht,Wt) is the grid the tiles run
                               over (= H,W; the OUTPUT dims for stride 2); finished by femasr_gn_finalize_rows */

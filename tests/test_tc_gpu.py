@@ -121,9 +121,23 @@ def test_tc_k_sliced_accumulation(cuda):
     nkb = 9 * Cin // 64
     for k0 in range(0, nkb, 4):
         G.tc_igemm(hi, lo, blob, bg if k0 == 0 else None, Cout, 3, res1=res if k0 == 0 else y, y=y, kb_begin=k0, kb_count=4)
-    e1, e2 = rel_err(G.nchw(one), want), rel_err(G.nchw(y), want)
-    print(f"K=2304 conv: single pass rel err {e1:.2e}, K-sliced {e2:.2e}")
+    res2 = res.clone()
+    y3 = G.tc_igemm(hi, lo, blob, bg, Cout, 3, res1=res2, y=res2, slice_kb=4)      # in-kernel slicing, in-place residual
+    e1, e2, e3 = rel_err(G.nchw(one), want), rel_err(G.nchw(y), want), rel_err(G.nchw(y3), want)
+    print(f"K=2304 conv: single pass rel err {e1:.2e}, K-sliced launches {e2:.2e}, in-kernel TMEM running sum {e3:.2e}")
     assert e2 <= 2e-6 and e2 < e1
+    assert e3 <= 2e-6 and e3 < e1
+    # linear K=1024 (fc2-like) and a partial last slice (K = 9*128/64 = 18 k-blocks, slices of 4)
+    xm, wm = rnd(777, 1024, seed=42), rnd(256, 1024, seed=43, scale=0.03)
+    wantm = F.linear(xm.double(), wm.double())
+    h2, l2 = G.tc_prepare(xm.view(1, 1, 777, 1024).to(cuda))
+    ym = G.tc_igemm(h2, l2, G.tc_pack(wm.view(256, 1024, 1, 1).to(cuda)), None, 256, 1, slice_kb=4)
+    assert rel_err(ym.view(777, 256), wantm) <= 1.5e-6
+    x5, w5 = rnd(1, 128, 20, 24, seed=44), rnd(128, 128, 3, 3, seed=45, scale=0.03)
+    want5 = F.conv2d(x5.double(), w5.double(), None, padding=1)
+    h5, l5 = G.tc_prepare(G.nhwc(x5).to(cuda))
+    y5 = G.tc_igemm(h5, l5, G.tc_pack(w5.to(cuda)), None, 128, 3, slice_kb=4)
+    assert rel_err(G.nchw(y5), want5) <= 1.5e-6
 
 
 def test_in_conv_split_planes(cuda):
