@@ -148,20 +148,68 @@ struct TcP {
 constexpr int TC_BM = 128, TC_BK = 64;
 constexpr int A_PLANE_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 
-template <int BN>
+// PAIR = true: two CTAs of a cluster (one TPC) cooperate on a 256 x BN tile with tcgen05 cta_group::2 - each
+// CTA stages its own 128 activation rows and only HALF of the weight tile, so the weight traffic per CTA (the
+// L2->SM bottleneck of the short-K / narrow layers) is halved and one more pipeline stage fits.
+template <int BN, bool PAIR>
 struct TcCfg {
-  static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * BN * TC_BK * 2;
-  static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;                 // weight-tile rows this CTA stages
+  static constexpr int B_PLANE_BYTES = B_ROWS * TC_BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
+  static constexpr int STAGES = PAIR ? (BN == 256 ? 3 : 4) : (BN == 256 ? 2 : (BN == 128 ? 3 : 4));
   static constexpr int EPI_BYTES = 8 * 2048 /*per-warp 32x16 fp32 transpose tiles*/ + 8 * 32 * 8 /*row offsets*/;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators; power of two for BN in {64,128,256}
 };
 
-template <int BN>
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  // non-.aligned forms: the role branches leave lane 0 of the producer / MMA warps diverged from its warp
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(384, 1)
 tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcP p) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -173,38 +221,61 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
 
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // CTA 0 of the pair issues the MMAs
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // m-tiles of 128 pixels; a pair-tile is two consecutive m-tiles (the second may fall off the end: dummy)
+  const int num_m = p.num_tiles / p.n_tiles;
+  const int num_work = PAIR ? ((num_m + 1) / 2) * p.n_tiles : p.num_tiles;
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), PAIR ? 512 : 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  const int nkb = p.taps * p.cchunks;
   const int ksz = p.taps == 9 ? 3 : 1;   // (p.up: taps == 4, offsets from the phase)
+
+  // work item -> (n-tile, m-tile of this CTA); decodes the m-tile into (phase, image, tile row/col)
+  struct TileCoord { int nt, tx, ty, b, ph; bool real; };
+  auto decode = [&](int work) {
+    TileCoord tc;
+    tc.nt = work % p.n_tiles;
+    int mt = work / p.n_tiles;
+    if (PAIR) mt = 2 * mt + (int)rank;
+    tc.real = mt < num_m;
+    tc.tx = mt % p.tiles_x; mt /= p.tiles_x;
+    tc.ty = mt % p.tiles_y; mt /= p.tiles_y;
+    tc.b = mt % p.B;
+    tc.ph = mt / p.B;                                // sub-pixel phase (0 unless p.up)
+    if (!tc.real) { tc.b = p.B; tc.ph = 0; tc.tx = 0; tc.ty = 0; }   // image index out of range: TMA zero-fills
+    return tc;
+  };
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles;
-      int mt = tile / p.n_tiles;
-      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y; mt /= p.tiles_y;
-      const int b = mt % p.B;
-      const int ph = mt / p.B;                       // sub-pixel phase (0 unless p.up)
-      const int py = ph >> 1, px = ph & 1;
-      const int x0 = tx * p.Wt, y0 = ty * p.Ht, n0 = ph * p.Cout + nt * BN;
+    for (int work = worker; work < num_work; work += nworkers) {
+      const TileCoord tc = decode(work);
+      const int py = tc.ph >> 1, px = tc.ph & 1;
+      const int x0 = tc.tx * p.Wt, y0 = tc.ty * p.Ht;
+      const int n0 = tc.ph * p.Cout + tc.nt * BN + (PAIR ? (int)rank * (BN / 2) : 0);
       for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
         const int tap = kb / p.cchunks;
         const int c0 = (kb - tap * p.cchunks) * TC_BK;
@@ -213,24 +284,34 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         else if (ksz == 3) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-        mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-        tma_load_4d(sa, &map_a_hi, full_bar(stage), c0, p.stride * x0 + dx, p.stride * y0 + dy, b);
-        tma_load_4d(sa + A_PLANE_BYTES, &map_a_lo, full_bar(stage), c0, p.stride * x0 + dx, p.stride * y0 + dy, b);
-        tma_load_2d(sa + 2 * A_PLANE_BYTES, &map_b_hi, full_bar(stage), tap * p.Cin + c0, n0);
-        tma_load_2d(sa + 2 * A_PLANE_BYTES + BN * TC_BK * 2, &map_b_lo, full_bar(stage), tap * p.Cin + c0, n0);
+        if (PAIR) {
+          // both CTAs' loads complete on the LEADER's barrier, armed once for the bytes of both
+          const uint32_t lead_full = map_to_cta(full_bar(stage), 0);
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+          tma2_load_4d(sa, &map_a_hi, lead_full, c0, p.stride * x0 + dx, p.stride * y0 + dy, tc.b);
+          tma2_load_4d(sa + A_PLANE_BYTES, &map_a_lo, lead_full, c0, p.stride * x0 + dx, p.stride * y0 + dy, tc.b);
+          tma2_load_2d(sa + 2 * A_PLANE_BYTES, &map_b_hi, lead_full, tap * p.Cin + c0, n0);
+          tma2_load_2d(sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &map_b_lo, lead_full, tap * p.Cin + c0, n0);
+        } else {
+          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          tma_load_4d(sa, &map_a_hi, full_bar(stage), c0, p.stride * x0 + dx, p.stride * y0 + dy, tc.b);
+          tma_load_4d(sa + A_PLANE_BYTES, &map_a_lo, full_bar(stage), c0, p.stride * x0 + dx, p.stride * y0 + dy, tc.b);
+          tma_load_2d(sa + 2 * A_PLANE_BYTES, &map_b_hi, full_bar(stage), tap * p.Cin + c0, n0);
+          tma_load_2d(sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &map_b_lo, full_bar(stage), tap * p.Cin + c0, n0);
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ===================== MMA issuer (leader CTA only when paired) =====================
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major both,
-    // N>>3 at bits 17-22, M>>4 at bits 24-28.
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    // N>>3 at bits 17-22, M>>4 at bits 24-28 (M = 256 across the CTA pair).
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     const bool sliced = p.slice_kb > 0;
     const int slice_len = sliced ? p.slice_kb : (p.kb_end - p.kb_begin);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int work = worker; work < num_work; work += nworkers) {
       for (int kb0 = p.kb_begin; kb0 < p.kb_end; kb0 += slice_len) {
         const int kb1 = min(kb0 + slice_len, p.kb_end);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -242,19 +323,28 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + A_PLANE_BYTES);
           const uint64_t b_hi = make_sw128_desc(sa + 2 * A_PLANE_BYTES);
-          const uint64_t b_lo = make_sw128_desc(sa + 2 * A_PLANE_BYTES + BN * TC_BK * 2);
+          const uint64_t b_lo = make_sw128_desc(sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             const uint64_t ko = (uint64_t)((k * 32) >> 4);   // +32 bytes per k-step inside the 128B swizzle atom
             // small cross terms first, the dominant hi*hi product last
-            umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
-            umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-            umma_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+            const uint32_t first = (kb != kb0 || k != 0) ? 1u : 0u;
+            if (PAIR) {
+              umma2_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+              umma2_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+              umma2_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+            } else {
+              umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+              umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+              umma_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+            }
           }
-          umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if (PAIR) umma2_commit_mc(empty_bar(stage)); else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));              // (partial) accumulator complete -> epilogue
+        // (partial) accumulator complete -> epilogue warps (of both CTAs)
+        if (PAIR) umma2_commit_mc(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
         // sliced: one MMA target buffer (0), the other holds the running sum; else ping-pong the two accumulators
         if (sliced) acc_phase ^= 1u;
         else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -281,15 +371,15 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     int acc = 0; uint32_t acc_phase = 0;
     const bool sliced = p.slice_kb > 0;
     const int nslices = sliced ? (p.kb_end - p.kb_begin + p.slice_kb - 1) / p.slice_kb : 1;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles;
-      int mt = tile / p.n_tiles;
-      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y; mt /= p.tiles_y;
-      const int b = mt % p.B;
-      const int ph = mt / p.B;
+    // the MMA issuer waits on the LEADER's tmem-empty barriers; the peer's epilogue arrives there remotely
+    auto release_acc = [&](int a) {
+      if (PAIR) mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0)); else mbar_arrive(tempty_bar(a));
+    };
+    for (int work = worker; work < num_work; work += nworkers) {
+      const TileCoord tc = decode(work);
+      const int nt = tc.nt, tx = tc.tx, ty = tc.ty, b = tc.b, ph = tc.ph;
       const int y = ty * p.Ht + (row >> p.wt_shift), x = tx * p.Wt + (row & (p.Wt - 1));
-      const bool valid = y < p.H && x < p.W;
+      const bool valid = tc.real && y < p.H && x < p.W;
       const int oy = p.up ? 2 * y + (ph >> 1) : y, ox = p.up ? 2 * x + (ph & 1) : x;
       const int Ho = p.up ? 2 * p.H : p.H, Wo = p.up ? 2 * p.W : p.W;
       const int col0 = nt * BN + half * (BN / 2);
@@ -325,7 +415,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(tempty_bar(0));
+        release_acc(0);
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -339,12 +429,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             nxt[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.res1 + offs[it] + c + CH) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         uint32_t r[16];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-            : "r"(t_row + (uint32_t)c) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_ld16(t_row + (uint32_t)c, r);
         if (nslices > 1) {
           uint32_t sr[16];
           tmem_ld16(t_sum + (uint32_t)c, sr);
@@ -407,11 +492,11 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           if (p.cpg == 8) {
             float s1 = sa + sb, s2 = ssa + ssb;
             s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-            if (lane == 0 || lane == 2) *reinterpret_cast<float2*>(gp + (ch0 / 8 + (lane >> 1)) * 2) = make_float2(s1, s2);
+            if (tc.real && (lane == 0 || lane == 2)) *reinterpret_cast<float2*>(gp + (ch0 / 8 + (lane >> 1)) * 2) = make_float2(s1, s2);
           } else if (p.cpg == 4) {
-            if (lane < 4) *reinterpret_cast<float2*>(gp + (ch0 / 4 + lane) * 2) = make_float2(sa + sb, ssa + ssb);
+            if (tc.real && lane < 4) *reinterpret_cast<float2*>(gp + (ch0 / 4 + lane) * 2) = make_float2(sa + sb, ssa + ssb);
           } else {
-            if (lane < 4) {
+            if (tc.real && lane < 4) {
               *reinterpret_cast<float2*>(gp + (ch0 / 2 + 2 * lane) * 2) = make_float2(sa, ssa);
               *reinterpret_cast<float2*>(gp + (ch0 / 2 + 2 * lane + 1) * 2) = make_float2(sb, ssb);
             }
@@ -422,16 +507,19 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));             // 256 arrivals release the accumulator
+      release_acc(acc);                         // 256 (512 when paired) arrivals release the accumulator
       if (sliced) acc_phase ^= 1u;
       else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -615,18 +703,31 @@ static int sm_count() {
   return g_sm_count;
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                      const TcP& p, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    FEMASR_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    FEMASR_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  tc_igemm_kernel<BN><<<grid, 384, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
-  return launch_status("tc_igemm_kernel");
+  if (!PAIR) {
+    const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    tc_igemm_kernel<BN, false><<<grid, 384, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
+    return launch_status("tc_igemm_kernel");
+  }
+  const int num_m = p.num_tiles / p.n_tiles;
+  const int work = ((num_m + 1) / 2) * p.n_tiles;
+  const int pairs = work < sm_count() / 2 ? work : sm_count() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  FEMASR_CUDA(cudaLaunchKernelEx(&cfg, tc_igemm_kernel<BN, true>, ah, al, bh, bl, p));
+  return launch_status("tc_igemm_kernel(pair)");
 }
 
 }  // namespace femasr
@@ -752,6 +853,9 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   p.tiles_x = (int)cdiv(W, p.Wt); p.tiles_y = (int)cdiv(H, p.Ht);
   const int BN = a->Cout % 256 == 0 ? 256 : (a->Cout % 128 == 0 ? 128 : 64);
   p.n_tiles = a->Cout / BN;
+  // CTA pairs (tcgen05 cta_group::2): a->pair 1 = on, 0 = off, -1 = library default (FEMASR_TC_PAIR, default off)
+  static const int pair_default = [] { const char* e = getenv("FEMASR_TC_PAIR"); return e ? atoi(e) : 0; }();
+  const bool pair = (a->pair < 0 ? pair_default : a->pair) != 0;
   const long ntile = (long)phases * B * p.tiles_x * p.tiles_y * p.n_tiles;
   FEMASR_CHECK_ARG(ntile < (1l << 31), "tc_igemm: too many tiles");
   p.num_tiles = (int)ntile; p.cchunks = a->Cin / 64;
@@ -776,14 +880,19 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   {
     const cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)phases * a->Cout};
     const cuuint64_t str[1] = {(cuuint64_t)Ktot * 2};
-    const cuuint32_t box[2] = {64, (cuuint32_t)BN};
+    const cuuint32_t box[2] = {64, (cuuint32_t)(pair ? BN / 2 : BN)};
     int s = make_map(&mbh, w_hi, 2, dims, str, box);
     if (s) return s;
     s = make_map(&mbl, w_lo, 2, dims, str, box);
     if (s) return s;
   }
   cudaStream_t st = as_stream(stream);
-  if (BN == 256) return launch_tc<256>(mah, mal, mbh, mbl, p, st);
-  if (BN == 128) return launch_tc<128>(mah, mal, mbh, mbl, p, st);
-  return launch_tc<64>(mah, mal, mbh, mbl, p, st);
+  if (pair) {
+    if (BN == 256) return launch_tc<256, true>(mah, mal, mbh, mbl, p, st);
+    if (BN == 128) return launch_tc<128, true>(mah, mal, mbh, mbl, p, st);
+    return launch_tc<64, true>(mah, mal, mbh, mbl, p, st);
+  }
+  if (BN == 256) return launch_tc<256, false>(mah, mal, mbh, mbl, p, st);
+  if (BN == 128) return launch_tc<128, false>(mah, mal, mbh, mbl, p, st);
+  return launch_tc<64, false>(mah, mal, mbh, mbl, p, st);
 }

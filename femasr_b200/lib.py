@@ -46,7 +46,7 @@ class TcArgs(C.Structure):
                 ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
                 ("ksize", C.c_int), ("act", C.c_int), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
                 ("stride", C.c_int), ("kb_begin", C.c_int), ("kb_count", C.c_int),
-                ("slice_kb", C.c_int), ("gn_partial", C.c_void_p), ("upsample", C.c_int)]
+                ("slice_kb", C.c_int), ("pair", C.c_int), ("gn_partial", C.c_void_p), ("upsample", C.c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/femasr_b200.h declares

@@ -163,6 +163,8 @@ typedef struct {
                               the tensor-core accumulator's truncation error to one slice */
   int slice_kb;            /* >0: the same slicing inside ONE launch - every slice_kb k-blocks the MMA accumulator is
                               drained into an fp32 running sum held in the second TMEM buffer (tcgen05.ld/st, RN adds) */
+  int pair;                /* 1: CTA pairs (tcgen05 cta_group::2, 256-row tiles, each CTA stages half the weight tile);
+                              0: single-CTA tiles; -1: library default */
   float* gn_partial;       /* optional: GroupNorm(32) partial sums of the OUTPUT, [B][rows][32][2] fp32 with
                               rows = femasr_tc_gn_partial_rows(Ht, Wt, upsample) where (Ht,Wt) is the grid the tiles run
                               over (= H,W; the OUTPUT dims for stride 2); finished by femasr_gn_finalize_rows */

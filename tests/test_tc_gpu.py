@@ -140,6 +140,27 @@ def test_tc_k_sliced_accumulation(cuda):
     assert rel_err(G.nchw(y5), want5) <= 1.5e-6
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,kw", [
+    (1, 24, 40, 256, 256, {}), (2, 16, 24, 128, 128, {}), (1, 33, 17, 128, 64, {}), (3, 64, 64, 64, 64, {}),
+    (1, 8, 8, 256, 256, {"upsample": 1}), (1, 31, 31, 256, 256, {"stride": 2}), (1, 24, 40, 256, 256, {"slice_kb": 4})])
+def test_tc_cta_pair(cuda, B, H, W, Cin, Cout, kw):
+    """tcgen05 cta_group::2 variant (256-row tiles over a CTA pair, odd tile counts -> dummy second tile)."""
+    x, w, b = rnd(B, Cin, H, W, seed=46), rnd(Cout, Cin, 3, 3, seed=47, scale=0.03), rnd(Cout, seed=48)
+    up, stride = kw.get("upsample", 0), kw.get("stride", 1)
+    xin = O.upsample2(x) if up else x
+    want = F.conv2d(xin.double(), w.double(), b.double(), stride=stride, padding=1)
+    res = rnd(*want.shape, seed=49).permute(0, 2, 3, 1).contiguous()
+    want = want + res.permute(0, 3, 1, 2).double()
+    hi, lo = G.tc_prepare(G.nhwc(x).to(cuda))
+    blob = G.tc_pack_up2(w.to(cuda)) if up else G.tc_pack(w.to(cuda))
+    y1 = G.tc_igemm(hi, lo, blob, b.to(cuda), Cout, 3, res1=res.to(cuda), pair=0, **kw)
+    y2 = G.tc_igemm(hi, lo, blob, b.to(cuda), Cout, 3, res1=res.to(cuda), pair=1, **kw)
+    e = rel_err(G.nchw(y2), want)
+    print(f"cta pair {B}x{H}x{W} {Cin}->{Cout} {kw}: rel err {e:.2e}, max |pair - single| {(y1 - y2).abs().max().item():.2e}")
+    assert e <= 2e-5
+    assert torch.equal(y1, y2), "same MMAs in the same order: the paired kernel must be bit-identical"
+
+
 def test_in_conv_split_planes(cuda):
     lib = L.load()
     B, H, W, cout = 2, 18, 23, 256
