@@ -224,9 +224,13 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // CTA 0 of the pair issues the MMAs
   const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  // m-tiles of 128 pixels; a pair-tile is two consecutive m-tiles (the second may fall off the end: dummy)
+  // m-tiles of 128 pixels; a pair-tile is two consecutive m-tiles of the SAME sub-pixel phase (the two CTAs share
+  // one weight tile); the second may fall off the end of the phase: dummy tile
   const int num_m = p.num_tiles / p.n_tiles;
-  const int num_work = PAIR ? ((num_m + 1) / 2) * p.n_tiles : p.num_tiles;
+  const int phases = p.up ? 4 : 1;
+  const int m_per_phase = num_m / phases;
+  const int pairs_per_phase = (m_per_phase + 1) / 2;
+  const int num_work = PAIR ? phases * pairs_per_phase * p.n_tiles : p.num_tiles;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -258,13 +262,18 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     TileCoord tc;
     tc.nt = work % p.n_tiles;
     int mt = work / p.n_tiles;
-    if (PAIR) mt = 2 * mt + (int)rank;
-    tc.real = mt < num_m;
+    tc.real = true;
+    if (PAIR) {
+      const int ph = mt / pairs_per_phase;
+      const int idx = 2 * (mt - ph * pairs_per_phase) + (int)rank;
+      tc.real = idx < m_per_phase;
+      mt = ph * m_per_phase + (tc.real ? idx : 0);
+    }
     tc.tx = mt % p.tiles_x; mt /= p.tiles_x;
     tc.ty = mt % p.tiles_y; mt /= p.tiles_y;
     tc.b = mt % p.B;
     tc.ph = mt / p.B;                                // sub-pixel phase (0 unless p.up)
-    if (!tc.real) { tc.b = p.B; tc.ph = 0; tc.tx = 0; tc.ty = 0; }   // image index out of range: TMA zero-fills
+    if (!tc.real) tc.b = p.B;                        // image index out of range: TMA zero-fills the dummy tile
     return tc;
   };
 
@@ -718,7 +727,8 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
     return launch_status("tc_igemm_kernel");
   }
   const int num_m = p.num_tiles / p.n_tiles;
-  const int work = ((num_m + 1) / 2) * p.n_tiles;
+  const int phases = p.up ? 4 : 1;
+  const int work = phases * ((num_m / phases + 1) / 2) * p.n_tiles;
   const int pairs = work < sm_count() / 2 ? work : sm_count() / 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
@@ -853,9 +863,12 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   p.tiles_x = (int)cdiv(W, p.Wt); p.tiles_y = (int)cdiv(H, p.Ht);
   const int BN = a->Cout % 256 == 0 ? 256 : (a->Cout % 128 == 0 ? 128 : 64);
   p.n_tiles = a->Cout / BN;
-  // CTA pairs (tcgen05 cta_group::2): a->pair 1 = on, 0 = off, -1 = library default (FEMASR_TC_PAIR, default off)
-  static const int pair_default = [] { const char* e = getenv("FEMASR_TC_PAIR"); return e ? atoi(e) : 0; }();
-  const bool pair = (a->pair < 0 ? pair_default : a->pair) != 0;
+  // CTA pairs (tcgen05 cta_group::2): a->pair 1 = on, 0 = off, -1 = automatic (FEMASR_TC_PAIR=0/1 overrides).
+  // Measured (profiles/microbench_*): pairing pays when the weight tile is wide and the K loop long enough to
+  // amortise the pair's coupling - BN = 256 and K >= 1024 (+10..22 %); narrow / short-K layers are faster unpaired.
+  static const int pair_env = [] { const char* e = getenv("FEMASR_TC_PAIR"); return e ? atoi(e) : -1; }();
+  const int pair_req = a->pair >= 0 ? a->pair : pair_env;
+  const bool pair = pair_req >= 0 ? pair_req != 0 : (BN == 256 && (long)taps * a->Cin >= 1024);
   const long ntile = (long)phases * B * p.tiles_x * p.tiles_y * p.n_tiles;
   FEMASR_CHECK_ARG(ntile < (1l << 31), "tc_igemm: too many tiles");
   p.num_tiles = (int)ntile; p.cchunks = a->Cin / 64;
