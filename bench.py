@@ -284,8 +284,16 @@ def main():
     achieved = d["flops"] / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0
     peak = peaks["tflops_sustained"] or peaks["tflops_burst"]
     tot_ms = sum(v["ms"] for v in prof.values())
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "tc_igemm_traffic_r1.json")
+    if dname == "tc_igemm" and os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic = int(tj["dram_bytes_per_launch"])
+        traffic_src = ("profiles/tc_igemm_traffic_r1.json: ncu dram__bytes_read.sum+dram__bytes_write.sum averaged over the "
+                       f"{tj['launches']} tc_igemm launches of one batch-32 step (L2->SM traffic is "
+                       f"{tj['l2_bytes_total'] / (tj['dram_read_bytes_total'] + tj['dram_write_bytes_total']):.1f}x that: the kernel is L2-bandwidth bound)")
     roofline = {"bound": "tensor", "kernel": dname, "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s",
-                "frac": round(achieved / peak, 4), "traffic": None,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peaks["source"] + ", cuBLAS bf16 sustained (kernel timed inside a long step)",
                 "launches_per_step": d["launches"] // 2, "avg_launch_ms": round(d["ms"] / max(1, d["launches"]), 4),
                 "share_of_step": round(d["ms"] / tot_ms, 4) if tot_ms else None,
