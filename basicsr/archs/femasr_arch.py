@@ -128,6 +128,13 @@ class FeMaSRNet(nn.Module):
             self._engine_sig = sig
         return self._engine
 
+    def __getstate__(self):
+        # the engine is a process-local native handle: copies / pickles rebuild it lazily from the parameters
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        state["_engine_sig"] = None
+        return state
+
     # ------------------------------------------------------------------ reference surface
     def encode_and_decode(self, input, gt_indices=None, current_iter=None):
         """femasr_arch.py:311-374 -> (out_img, codebook_loss, semantic_loss, [indices])."""

@@ -65,3 +65,19 @@ def test_unsupported_configs_raise():
         FeMaSRNet(codebook_params=[[32, 1024, 256]], LQ_stage=False)
     with pytest.raises(NotImplementedError):
         FeMaSRNet(codebook_params=[[32, 1024, 256], [64, 512, 256]], LQ_stage=True)
+
+
+def test_module_copy_and_checkpoint_roundtrip(tmp_path):
+    import copy
+    from basicsr.archs.femasr_arch import FeMaSRNet
+    net = FeMaSRNet(codebook_params=[[32, 1024, 256]], LQ_stage=True, scale_factor=2).eval()
+    net._engine = object()          # stands in for a live native handle
+    clone = copy.deepcopy(net)
+    assert clone._engine is None and clone._engine_sig is None
+    path = tmp_path / "w.pth"
+    torch.save({"params": net.state_dict()}, path)            # the reference's checkpoint format (base_model.py:212-239)
+    other = FeMaSRNet(codebook_params=[[32, 1024, 256]], LQ_stage=True, scale_factor=2)
+    missing = other.load_state_dict(torch.load(path)["params"], strict=False)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, other.state_dict()[k])
