@@ -285,7 +285,7 @@ struct Ctx {
       t.bias = P(wname + ".bias");
       t.res1 = res1; t.res2 = res2; t.y = y; t.out_hi = out_hi; t.out_lo = out_lo; t.gn_partial = gn_partial;
       t.B = B; t.H = Hin; t.W = Win; t.Cin = Cin; t.Cout = Cout; t.ksize = ksize; t.act = act; t.upsample = upsample;
-      t.stride = stride; t.pair = -1;
+      t.stride = stride; t.pair = -1; t.strip = -1;
       const int u = upsample ? 2 : 1;
       const int Ho = stride == 2 ? (Hin - 1) / 2 + 1 : Hin * u, Wo = stride == 2 ? (Win - 1) / 2 + 1 : Win * u;
       const double flops = 2.0 * B * Ho * (double)Wo * Cout * Cin * ksize * ksize;   // algorithmic (reference) count
@@ -311,9 +311,15 @@ struct Ctx {
 
   // GroupNorm partial sums produced by a tensor-core conv epilogue (see femasr_tc_args.gn_partial)
   struct Stats { float* partial = nullptr; int rows = 0; };
-  Stats alloc_stats(int B, int H, int W, int upsample) {     // H,W: conv-input (low-res if upsample) size
+  // for the tensor-core conv [B,H,W,Cin] -> Cout (H,W: conv-input size, low-res if upsample) that will produce them
+  Stats alloc_stats(int B, int H, int W, int Cin, int Cout, int upsample, int stride) {
+    femasr_tc_args t;
+    memset(&t, 0, sizeof(t));
+    t.B = B; t.H = H; t.W = W; t.Cin = Cin; t.Cout = Cout; t.ksize = 3; t.upsample = upsample; t.stride = stride;
+    t.pair = -1; t.strip = -1;
+    t.slice_kb = (precise_region && net->tc_precise && (upsample ? 4 : 9) * (Cin / 64) > 4) ? 4 : 0;
     Stats st_;
-    st_.rows = femasr_tc_gn_partial_rows(H, W, upsample);
+    st_.rows = femasr_tc_gn_partial_rows(&t);
     st_.partial = ar.alloc((size_t)B * st_.rows * 32 * 2);
     return st_;
   }
@@ -344,7 +350,7 @@ struct Ctx {
     gn_tables(p + ".conv.0.norm", x, sx, sc, sh, B, H * W, C);
     if (sx.partial) ar.release(sx.partial);
     Stats s1, s2;
-    if (tc) s1 = alloc_stats(B, H, W, 0);
+    if (tc) s1 = alloc_stats(B, H, W, C, C, 0, 1);
     if (tc)
       conv_tc(p + ".conv.2", x, t, B, H, W, C, C, 3, 0, FEMASR_PRO_GN_SILU, sc, sh, nullptr, nullptr, 0, nullptr, nullptr,
               nullptr, nullptr, nullptr, nullptr, s1.partial);
@@ -352,7 +358,7 @@ struct Ctx {
       conv(p + ".conv.2", x, t, B, H, W, C, C, 3, 1, 0, FEMASR_PRO_GN_SILU, sc, sh, nullptr, nullptr, 0, nullptr, nullptr);
     gn_tables(p + ".conv.3.norm", t, s1, sc, sh, B, H * W, C);
     if (s1.partial) ar.release(s1.partial);
-    if (tc && want_out) s2 = alloc_stats(B, H, W, 0);
+    if (tc && want_out) s2 = alloc_stats(B, H, W, C, C, 0, 1);
     if (tc)
       conv_tc(p + ".conv.5", t, x, B, H, W, C, C, 3, 0, FEMASR_PRO_GN_SILU, sc, sh, nullptr, nullptr, 0, x, extra,
               nullptr, nullptr, nullptr, nullptr, s2.partial);
@@ -368,7 +374,7 @@ struct Ctx {
     float* y = ar.alloc((size_t)B * 2 * H * 2 * W * Cout);
     Stats s0;
     if (tc_convs(Cin) && tc_convs(Cout) && (dry() || net->tcw_up.count(pconv + ".weight"))) {
-      s0 = alloc_stats(B, H, W, 1);
+      s0 = alloc_stats(B, H, W, Cin, Cout, 1, 1);
       conv_tc(pconv, x, y, B, H, W, Cin, Cout, 3, 1, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
               nullptr, nullptr, nullptr, nullptr, s0.partial);
     } else {
@@ -488,7 +494,7 @@ struct Ctx {
       float* nxt = ar.alloc((size_t)B * ho * wo * co);
       Stats sd0;
       if (tc) {
-        sd0 = alloc_stats(B, ho, wo, 0);
+        sd0 = alloc_stats(B, h, w, c, co, 0, 2);
         conv_tc(b + ".0", cur, nxt, B, h, w, c, co, 3, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
                 i == 0 ? in_hi : nullptr, i == 0 ? in_lo : nullptr, nullptr, nullptr, sd0.partial, 2);
       } else {

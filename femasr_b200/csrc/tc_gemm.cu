@@ -151,15 +151,32 @@ constexpr int A_PLANE_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 // PAIR = true: two CTAs of a cluster (one TPC) cooperate on a 256 x BN tile with tcgen05 cta_group::2 - each
 // CTA stages its own 128 activation rows and only HALF of the weight tile, so the weight traffic per CTA (the
 // L2->SM bottleneck of the short-K / narrow layers) is halved and one more pipeline stage fits.
-template <int BN, bool PAIR>
+// STRIP = true (3x3 stride-1 convs on maps at least 128 wide, BN <= 128): the tile is one image row of 128 pixels
+// and the activation operand of the three horizontal taps (kw = 0,1,2) is ONE shared-memory strip of 130 pixels per
+// (kh, 64-channel chunk): tap kw reads it through a descriptor that starts kw rows (kw*128 B) into the strip, with the
+// descriptor's base-offset field carrying the swizzle phase.  Activation traffic from L2 drops 2.9x (3 loads
+// instead of 9 per chunk) - the narrow layers are L2->SM bound (profiles/tc_igemm_traffic_r1.json).  Weights stream
+// through their own ring, one tap per stage.
+constexpr int STRIP_PX = 130;                         // 128 outputs + one halo pixel each side
+constexpr int STRIP_PLANE_BYTES = 17 * 1024;          // 130 rows x 128 B = 16,640 B, padded to the 1024-B swizzle period
+
+template <int BN, bool PAIR, bool STRIP>
 struct TcCfg {
+  static_assert(!(PAIR && STRIP), "strip tiles are single-CTA");
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;                 // weight-tile rows this CTA stages
   static constexpr int B_PLANE_BYTES = B_ROWS * TC_BK * 2;
+  // joint A+B stages (normal / pair)
   static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
   static constexpr int STAGES = PAIR ? (BN == 256 ? 3 : 4) : (BN == 256 ? 2 : (BN == 128 ? 3 : 4));
+  // separate rings (strip)
+  static constexpr int SA_STAGES = 2, SA_BYTES = 2 * STRIP_PLANE_BYTES;
+  static constexpr int SB_STAGES = BN == 64 ? 6 : 4, SB_BYTES = 2 * B_PLANE_BYTES;
+  static constexpr int PIPE_BYTES = STRIP ? SA_STAGES * SA_BYTES + SB_STAGES * SB_BYTES : STAGES * STAGE_BYTES;
+  static constexpr int NBAR_PIPE = STRIP ? 2 * SA_STAGES + 2 * SB_STAGES : 2 * STAGES;   // full/empty barriers of the rings
   static constexpr int EPI_BYTES = 8 * 2048 /*per-warp 32x16 fp32 transpose tiles*/ + 8 * 32 * 8 /*row offsets*/;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+  static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators; power of two for BN in {64,128,256}
+  static_assert(8 * (NBAR_PIPE + 4) + 4 <= 256, "barrier area");
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -205,21 +222,26 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool STRIP>
 __global__ void __launch_bounds__(384, 1)
 tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcP p) {
-  using Cfg = TcCfg<BN, PAIR>;
+  using Cfg = TcCfg<BN, PAIR, STRIP>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-  // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base pointer
+  const uint32_t bar_base = smem_base + Cfg::PIPE_BYTES;
+  // barriers: the ring barriers (joint: full[STAGES], empty[STAGES]; strip: fullA, emptyA, fullB, emptyB),
+  // then tmem_full[2], tmem_empty[2]; then the TMEM base pointer
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto fullA_bar = [&](int s) { return bar_base + 8u * s; };
+  auto emptyA_bar = [&](int s) { return bar_base + 8u * (Cfg::SA_STAGES + s); };
+  auto fullB_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::SA_STAGES + s); };
+  auto emptyB_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::SA_STAGES + Cfg::SB_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (Cfg::NBAR_PIPE + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (Cfg::NBAR_PIPE + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (Cfg::NBAR_PIPE + 4);
 
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // CTA 0 of the pair issues the MMAs
   const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -234,7 +256,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < Cfg::NBAR_PIPE; ++s) mbar_init(bar_base + 8u * s, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), PAIR ? 512 : 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -277,7 +299,75 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     return tc;
   };
 
-  if (warp == 0 && lane == 0) {
+  if (STRIP && warp == 0 && lane == 0) {
+    // ===================== TMA producer (strip mode) =====================
+    // per (kh, 64-channel chunk): one 130-pixel activation strip (hi, lo), then the three taps' weight tiles
+    int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+    for (int work = worker; work < num_work; work += nworkers) {
+      const TileCoord tc = decode(work);
+      const int x0 = tc.tx * p.Wt, y0 = tc.ty, n0 = tc.nt * BN;
+      for (int kh = 0; kh < 3; ++kh)
+        for (int cc = 0; cc < p.cchunks; ++cc) {
+          const int c0 = cc * TC_BK;
+          mbar_wait(emptyA_bar(sa), pa ^ 1u);
+          const uint32_t a_dst = smem_base + sa * Cfg::SA_BYTES;
+          mbar_expect_tx(fullA_bar(sa), 2 * STRIP_PX * TC_BK * 2);
+          tma_load_4d(a_dst, &map_a_hi, fullA_bar(sa), c0, x0 - 1, y0 + kh - 1, tc.b);
+          tma_load_4d(a_dst + STRIP_PLANE_BYTES, &map_a_lo, fullA_bar(sa), c0, x0 - 1, y0 + kh - 1, tc.b);
+          if (++sa == Cfg::SA_STAGES) { sa = 0; pa ^= 1u; }
+          for (int kw = 0; kw < 3; ++kw) {
+            const int tap = kh * 3 + kw;
+            mbar_wait(emptyB_bar(sb), pb ^ 1u);
+            const uint32_t b_dst = smem_base + Cfg::SA_STAGES * Cfg::SA_BYTES + sb * Cfg::SB_BYTES;
+            mbar_expect_tx(fullB_bar(sb), Cfg::SB_BYTES);
+            tma_load_2d(b_dst, &map_b_hi, fullB_bar(sb), tap * p.Cin + c0, n0);
+            tma_load_2d(b_dst + Cfg::B_PLANE_BYTES, &map_b_lo, fullB_bar(sb), tap * p.Cin + c0, n0);
+            if (++sb == Cfg::SB_STAGES) { sb = 0; pb ^= 1u; }
+          }
+        }
+    }
+  } else if (STRIP && warp == 1 && lane == 0) {
+    // ===================== MMA issuer (strip mode) =====================
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int work = worker; work < num_work; work += nworkers) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      uint32_t first = 0u;
+      for (int kh = 0; kh < 3; ++kh)
+        for (int cc = 0; cc < p.cchunks; ++cc) {
+          mbar_wait(fullA_bar(sa), pa);
+          tc_fence_after();
+          const uint32_t a_base = smem_base + sa * Cfg::SA_BYTES;
+          for (int kw = 0; kw < 3; ++kw) {
+            mbar_wait(fullB_bar(sb), pb);
+            tc_fence_after();
+            const uint32_t b_base = smem_base + Cfg::SA_STAGES * Cfg::SA_BYTES + sb * Cfg::SB_BYTES;
+            // tap kw = the strip shifted by kw pixel rows; base-offset field (bits 49-51) = swizzle phase of the start row
+            const uint64_t shift = (uint64_t)kw << 49;
+            const uint64_t a_hi = make_sw128_desc(a_base + kw * 128) | shift;
+            const uint64_t a_lo = make_sw128_desc(a_base + STRIP_PLANE_BYTES + kw * 128) | shift;
+            const uint64_t b_hi = make_sw128_desc(b_base), b_lo = make_sw128_desc(b_base + Cfg::B_PLANE_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t ko = (uint64_t)((k * 32) >> 4);
+              umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+              first = 1u;
+              umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+              umma_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+            }
+            umma_commit(emptyB_bar(sb));
+            if (++sb == Cfg::SB_STAGES) { sb = 0; pb ^= 1u; }
+          }
+          umma_commit(emptyA_bar(sa));
+          if (++sa == Cfg::SA_STAGES) { sa = 0; pa ^= 1u; }
+        }
+      umma_commit(tfull_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else if (!STRIP && warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     int stage = 0; uint32_t phase = 0;
     for (int work = worker; work < num_work; work += nworkers) {
@@ -311,7 +401,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
+  } else if (!STRIP && warp == 1 && lane == 0 && rank == 0) {
     // ===================== MMA issuer (leader CTA only when paired) =====================
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major both,
     // N>>3 at bits 17-22, M>>4 at bits 24-28 (M = 256 across the CTA pair).
@@ -712,32 +802,33 @@ static int sm_count() {
   return g_sm_count;
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool STRIP>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                      const TcP& p, cudaStream_t st) {
-  using Cfg = TcCfg<BN, PAIR>;
+  using Cfg = TcCfg<BN, PAIR, STRIP>;
   static bool attr_set = false;
   if (!attr_set) {
-    FEMASR_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    FEMASR_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<BN, PAIR, STRIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  if (!PAIR) {
+  if constexpr (!PAIR) {
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    tc_igemm_kernel<BN, false><<<grid, 384, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
+    tc_igemm_kernel<BN, false, STRIP><<<grid, 384, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
     return launch_status("tc_igemm_kernel");
+  } else {
+    const int num_m = p.num_tiles / p.n_tiles;
+    const int phases = p.up ? 4 : 1;
+    const int work = phases * ((num_m / phases + 1) / 2) * p.n_tiles;
+    const int pairs = work < sm_count() / 2 ? work : sm_count() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    FEMASR_CUDA(cudaLaunchKernelEx(&cfg, tc_igemm_kernel<BN, true, false>, ah, al, bh, bl, p));
+    return launch_status("tc_igemm_kernel(pair)");
   }
-  const int num_m = p.num_tiles / p.n_tiles;
-  const int phases = p.up ? 4 : 1;
-  const int work = phases * ((num_m / phases + 1) / 2) * p.n_tiles;
-  const int pairs = work < sm_count() / 2 ? work : sm_count() / 2;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  FEMASR_CUDA(cudaLaunchKernelEx(&cfg, tc_igemm_kernel<BN, true>, ah, al, bh, bl, p));
-  return launch_status("tc_igemm_kernel(pair)");
 }
 
 }  // namespace femasr
@@ -754,11 +845,43 @@ static void tc_tile_shape(int H, int W, int* Wt, int* Ht) {
   *Wt = best_wt; *Ht = 128 / best_wt;
 }
 
-// rows of GroupNorm partials femasr_tc_igemm writes per image for a conv on an [H,W] (low-res if upsample) input
-extern "C" int femasr_tc_gn_partial_rows(int H, int W, int upsample) {
-  int wt, ht;
-  tc_tile_shape(H, W, &wt, &ht);
-  return (upsample ? 4 : 1) * (int)cdiv(W, wt) * (int)cdiv(H, ht) * 4;
+// Tiling decisions shared by femasr_tc_igemm and femasr_tc_gn_partial_rows.  (H, W) = the grid the tiles run over.
+struct TilePlan { int Wt, Ht, wt_shift, tiles_x, tiles_y, BN; bool pair, strip; };
+static TilePlan plan_tiles(const femasr_tc_args* a, int H, int W) {
+  TilePlan t;
+  const int stride = a->stride == 2 ? 2 : 1;
+  const int taps = a->upsample ? 4 : a->ksize * a->ksize;
+  t.BN = a->Cout % 256 == 0 ? 256 : (a->Cout % 128 == 0 ? 128 : 64);
+  // CTA pairs (tcgen05 cta_group::2): a->pair 1 = on, 0 = off, -1 = automatic (FEMASR_TC_PAIR=0/1 overrides).
+  // Measured (profiles/microbench_*): pairing pays when the weight tile is wide and the K loop long enough to
+  // amortise the pair's coupling - BN = 256 and K >= 1024 (+10..22 %); narrow / short-K layers are faster unpaired.
+  static const int pair_env = [] { const char* e = getenv("FEMASR_TC_PAIR"); return e ? atoi(e) : -1; }();
+  const int pair_req = a->pair >= 0 ? a->pair : pair_env;
+  t.pair = pair_req >= 0 ? pair_req != 0 : (t.BN == 256 && (long)taps * a->Cin >= 1024);
+  // strip mode (one activation strip shared by the three horizontal taps): a->strip 1/0/-1 like pair
+  static const int strip_env = [] { const char* e = getenv("FEMASR_TC_STRIP"); return e ? atoi(e) : -1; }();
+  const int strip_req = a->strip >= 0 ? a->strip : strip_env;
+  const bool strip_ok = a->ksize == 3 && stride == 1 && !a->upsample && t.BN <= 128 && W >= 128 && a->kb_begin == 0 &&
+                        a->kb_count == 0 && a->slice_kb == 0;
+  t.strip = strip_ok && (strip_req >= 0 ? strip_req != 0 : true);
+  if (t.strip) {
+    t.pair = false;
+    t.Wt = 128; t.Ht = 1;
+  } else {
+    tc_tile_shape(H, W, &t.Wt, &t.Ht);   // the widest power-of-two Wt <= 128 that wastes the fewest padded pixels
+  }
+  t.wt_shift = 0; while ((1 << t.wt_shift) < t.Wt) ++t.wt_shift;
+  t.tiles_x = (int)cdiv(W, t.Wt); t.tiles_y = (int)cdiv(H, t.Ht);
+  return t;
+}
+
+// rows of GroupNorm partials femasr_tc_igemm will write per image for this conv (same decision logic as the launch)
+extern "C" int femasr_tc_gn_partial_rows(const femasr_tc_args* a) {
+  if (!a) return 0;
+  int H = a->H, W = a->W;
+  if (a->stride == 2) { H = (H - 1) / 2 + 1; W = (W - 1) / 2 + 1; }
+  const TilePlan t = plan_tiles(a, H, W);
+  return (a->upsample ? 4 : 1) * t.tiles_x * t.tiles_y * 4;
 }
 
 extern "C" size_t femasr_tc_weight_bytes(int Cout, int Cin, int kh, int kw) {
@@ -857,18 +980,12 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
                    "tc_igemm: gn_partial needs a 3x3 conv with Cout in {64,128,256}");
   p.B = B; p.H = H; p.W = W; p.Cin = a->Cin; p.Cout = a->Cout; p.taps = taps; p.act = a->act;
   p.up = a->upsample ? 1 : 0; p.stride = stride;
-  // tile shape: the widest power-of-two Wt <= 128 that wastes the fewest padded pixels
-  tc_tile_shape(H, W, &p.Wt, &p.Ht);
-  p.wt_shift = 0; while ((1 << p.wt_shift) < p.Wt) ++p.wt_shift;
-  p.tiles_x = (int)cdiv(W, p.Wt); p.tiles_y = (int)cdiv(H, p.Ht);
-  const int BN = a->Cout % 256 == 0 ? 256 : (a->Cout % 128 == 0 ? 128 : 64);
+  const TilePlan plan = plan_tiles(a, H, W);
+  p.Wt = plan.Wt; p.Ht = plan.Ht; p.wt_shift = plan.wt_shift; p.tiles_x = plan.tiles_x; p.tiles_y = plan.tiles_y;
+  const int BN = plan.BN;
   p.n_tiles = a->Cout / BN;
-  // CTA pairs (tcgen05 cta_group::2): a->pair 1 = on, 0 = off, -1 = automatic (FEMASR_TC_PAIR=0/1 overrides).
-  // Measured (profiles/microbench_*): pairing pays when the weight tile is wide and the K loop long enough to
-  // amortise the pair's coupling - BN = 256 and K >= 1024 (+10..22 %); narrow / short-K layers are faster unpaired.
-  static const int pair_env = [] { const char* e = getenv("FEMASR_TC_PAIR"); return e ? atoi(e) : -1; }();
-  const int pair_req = a->pair >= 0 ? a->pair : pair_env;
-  const bool pair = pair_req >= 0 ? pair_req != 0 : (BN == 256 && (long)taps * a->Cin >= 1024);
+  const bool pair = plan.pair, strip = plan.strip;
+  FEMASR_CHECK_ARG(!(a->strip == 1 && !strip), "tc_igemm: strip mode needs a plain 3x3 stride-1 conv, Cout tile <= 128, W >= 128, no K slicing");
   const long ntile = (long)phases * B * p.tiles_x * p.tiles_y * p.n_tiles;
   FEMASR_CHECK_ARG(ntile < (1l << 31), "tc_igemm: too many tiles");
   p.num_tiles = (int)ntile; p.cchunks = a->Cin / 64;
@@ -884,7 +1001,7 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
     const cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
     const cuuint64_t str[3] = {(cuuint64_t)a->Cin * 2, (cuuint64_t)Win * a->Cin * 2, (cuuint64_t)Hin * Win * a->Cin * 2};
     // with a traversal stride s the box spans s*Wt x s*Ht source pixels and lands Wt x Ht of them in smem
-    const cuuint32_t box[4] = {64, (cuuint32_t)(p.Wt * stride), (cuuint32_t)(p.Ht * stride), 1};
+    const cuuint32_t box[4] = {64, (cuuint32_t)(strip ? STRIP_PX : p.Wt * stride), (cuuint32_t)(p.Ht * stride), 1};
     int s = make_map(&mah, a->a_hi, 4, dims, str, box, stride);
     if (s) return s;
     s = make_map(&mal, a->a_lo, 4, dims, str, box, stride);
@@ -900,12 +1017,16 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
     if (s) return s;
   }
   cudaStream_t st = as_stream(stream);
-  if (pair) {
-    if (BN == 256) return launch_tc<256, true>(mah, mal, mbh, mbl, p, st);
-    if (BN == 128) return launch_tc<128, true>(mah, mal, mbh, mbl, p, st);
-    return launch_tc<64, true>(mah, mal, mbh, mbl, p, st);
+  if (strip) {
+    if (BN == 128) return launch_tc<128, false, true>(mah, mal, mbh, mbl, p, st);
+    return launch_tc<64, false, true>(mah, mal, mbh, mbl, p, st);
   }
-  if (BN == 256) return launch_tc<256, false>(mah, mal, mbh, mbl, p, st);
-  if (BN == 128) return launch_tc<128, false>(mah, mal, mbh, mbl, p, st);
-  return launch_tc<64, false>(mah, mal, mbh, mbl, p, st);
+  if (pair) {
+    if (BN == 256) return launch_tc<256, true, false>(mah, mal, mbh, mbl, p, st);
+    if (BN == 128) return launch_tc<128, true, false>(mah, mal, mbh, mbl, p, st);
+    return launch_tc<64, true, false>(mah, mal, mbh, mbl, p, st);
+  }
+  if (BN == 256) return launch_tc<256, false, false>(mah, mal, mbh, mbl, p, st);
+  if (BN == 128) return launch_tc<128, false, false>(mah, mal, mbh, mbl, p, st);
+  return launch_tc<64, false, false>(mah, mal, mbh, mbl, p, st);
 }

@@ -46,7 +46,8 @@ class TcArgs(C.Structure):
                 ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
                 ("ksize", C.c_int), ("act", C.c_int), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
                 ("stride", C.c_int), ("kb_begin", C.c_int), ("kb_count", C.c_int),
-                ("slice_kb", C.c_int), ("pair", C.c_int), ("gn_partial", C.c_void_p), ("upsample", C.c_int)]
+                ("slice_kb", C.c_int), ("pair", C.c_int), ("strip", C.c_int), ("gn_partial", C.c_void_p),
+                ("upsample", C.c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/femasr_b200.h declares
@@ -77,7 +78,7 @@ SIGNATURES = {
     "femasr_tc_pack_weight_up2": (_I, [_V, _V, _I, _I, _V]),
     "femasr_tc_prepare": (_I, [_V, _V, _V, _I, _V, _V, _V, _V, _I, _I, _I, _I, _I, _F, _V]),
     "femasr_tc_igemm": (_I, [C.POINTER(TcArgs), _V]),
-    "femasr_tc_gn_partial_rows": (_I, [_I, _I, _I]),
+    "femasr_tc_gn_partial_rows": (_I, [C.POINTER(TcArgs)]),
     "femasr_gn_finalize_rows": (_I, [_V, _V, _V, _V, _V, _I, _I, _I, _I, _F, _V]),
     "femasr_gn_scratch_floats": (_Z, [_I, _I, _I]),
     "femasr_gn_stats": (_I, [_V, _V, _V, _V, _V, _V, _I, _I, _I, _F, _V]),

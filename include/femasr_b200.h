@@ -165,9 +165,11 @@ typedef struct {
                               drained into an fp32 running sum held in the second TMEM buffer (tcgen05.ld/st, RN adds) */
   int pair;                /* 1: CTA pairs (tcgen05 cta_group::2, 256-row tiles, each CTA stages half the weight tile);
                               0: single-CTA tiles; -1: library default */
+  int strip;               /* 1: row-strip tiles (one image row of 128 pixels; the three horizontal taps share one
+                              130-pixel activation strip in shared memory): plain 3x3 stride-1 convs, Cout tile <= 128,
+                              W >= 128, no K slicing.  0: off; -1: automatic */
   float* gn_partial;       /* optional: GroupNorm(32) partial sums of the OUTPUT, [B][rows][32][2] fp32 with
-                              rows = femasr_tc_gn_partial_rows(Ht, Wt, upsample) where (Ht,Wt) is the grid the tiles run
-                              over (= H,W; the OUTPUT dims for stride 2); finished by femasr_gn_finalize_rows */
+                              rows = femasr_tc_gn_partial_rows(args); finished by femasr_gn_finalize_rows */
   int upsample;            /* 1: y [B,2H,2W,Cout] = conv3x3(nearest_x2(a)), evaluated as 4 sub-pixel 2x2 convs on the
                               low-res grid; a_* are at the LOW resolution and w_blob comes from femasr_tc_pack_weight_up2 */
 } femasr_tc_args;
@@ -181,7 +183,9 @@ int femasr_tc_prepare(const float* x, void* a_hi, void* a_lo, int mode, const fl
                       const float* gamma, const float* beta, int B, int H, int W, int C, int upsample,
                       float eps, void* stream);
 int femasr_tc_igemm(const femasr_tc_args* a, void* stream);
-int femasr_tc_gn_partial_rows(int H, int W, int upsample);
+/* number of GroupNorm partial rows per image femasr_tc_igemm will write for these arguments (the tiling is
+ * chosen from the shape / flags; pointers in `a` are not read) */
+int femasr_tc_gn_partial_rows(const femasr_tc_args* a);
 /* scale/shift tables (as femasr_gn_stats) from the partial rows a femasr_tc_igemm epilogue produced;
  * HW = pixels per image of the tensor the partials describe. */
 int femasr_gn_finalize_rows(const float* partial, const float* gamma, const float* beta, float* scale, float* shift,

@@ -26,6 +26,7 @@ def timeit(fn, reps=5):
 
 
 PAIR = int(os.environ.get('MB_PAIR', '-1'))
+STRIP = int(os.environ.get('MB_STRIP', '-1'))
 
 
 def conv_case(name, B, H, W, Cin, Cout, ksize=3, up=0, res=False, act=0, split=False, bias=True):
@@ -37,7 +38,7 @@ def conv_case(name, B, H, W, Cin, Cout, ksize=3, up=0, res=False, act=0, split=F
     u = 2 if up else 1
     y = None if split else torch.empty(B, H * u, W * u, Cout, device=dev)
     r = torch.randn(B, H * u, W * u, Cout, device=dev) if res else None
-    fn = lambda: G.tc_igemm(hi, lo, blob, b, Cout, ksize, act=act, res1=r, y=y, upsample=up, split_out=split, pair=PAIR)
+    fn = lambda: G.tc_igemm(hi, lo, blob, b, Cout, ksize, act=act, res1=r, y=y, upsample=up, split_out=split, pair=PAIR, strip=STRIP)
     ms = timeit(fn)
     flops = 2.0 * B * H * u * W * u * Cout * Cin * ksize * ksize
     execd = 3 * 2.0 * B * H * W * Cout * Cin * (4 * 4 if up else ksize * ksize)

@@ -96,7 +96,7 @@ def tc_pack_up2(w_oihw):
 
 
 def tc_igemm(hi, lo, blob, bias, Cout, ksize=3, act=0, res1=None, res2=None, y=None, upsample=0, split_out=False,
-             gn_partial=None, stride=1, kb_begin=0, kb_count=0, slice_kb=0, pair=-1):
+             gn_partial=None, stride=1, kb_begin=0, kb_count=0, slice_kb=0, pair=-1, strip=-1):
     lib = L.load()
     B, H, W, Cin = hi.shape
     u = 2 if upsample else 1
@@ -108,6 +108,12 @@ def tc_igemm(hi, lo, blob, bias, Cout, ksize=3, act=0, res1=None, res2=None, y=N
     elif y is None:
         y = torch.empty(B, Ho, Wo, Cout, device=hi.device)
     a = L.TcArgs(p(hi), p(lo), p(blob), p(bias), p(res1), p(res2), p(y), B, H, W, Cin, Cout, ksize, act,
-                 p(oh), p(ol), stride, kb_begin, kb_count, slice_kb, pair, p(gn_partial), upsample)
+                 p(oh), p(ol), stride, kb_begin, kb_count, slice_kb, pair, strip, p(gn_partial), upsample)
     L.check(lib.femasr_tc_igemm(C.byref(a), S()))
     return (oh, ol) if split_out else y
+
+
+def tc_gn_rows(B, H, W, Cin, Cout, upsample=0, stride=1, slice_kb=0, pair=-1, strip=-1):
+    a = L.TcArgs(None, None, None, None, None, None, None, B, H, W, Cin, Cout, 3, 0, None, None, stride, 0, 0,
+                 slice_kb, pair, strip, None, upsample)
+    return L.load().femasr_tc_gn_partial_rows(C.byref(a))

@@ -72,7 +72,8 @@ def test_tc_upsample_conv_subpixel(cuda, B, H, W, Cin, Cout):
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,up", [(2, 24, 40, 64, 64, 0), (1, 33, 17, 128, 128, 0), (2, 16, 16, 256, 256, 0),
-                                              (1, 12, 20, 256, 128, 1), (2, 9, 72, 128, 64, 1)])
+                                              (1, 12, 20, 256, 128, 1), (2, 9, 72, 128, 64, 1), (1, 5, 200, 64, 64, 0),
+                                              (2, 3, 256, 128, 128, 0)])
 def test_tc_epilogue_groupnorm_partials(cuda, B, H, W, Cin, Cout, up):
     """GroupNorm statistics of the conv OUTPUT accumulated in the epilogue == a stats pass over the stored output."""
     lib = L.load()
@@ -80,7 +81,7 @@ def test_tc_epilogue_groupnorm_partials(cuda, B, H, W, Cin, Cout, up):
     u = 2 if up else 1
     res = rnd(B, u * H, u * W, Cout, seed=30).to(cuda)
     gamma, beta = (1 + 0.2 * rnd(Cout, seed=31)).to(cuda), (0.2 * rnd(Cout, seed=32)).to(cuda)
-    rows = lib.femasr_tc_gn_partial_rows(H, W, up)
+    rows = G.tc_gn_rows(B, H, W, Cin, Cout, upsample=up)
     part = torch.full((B, rows, 32, 2), float("nan"), device=cuda)
     hi, lo = G.tc_prepare(G.nhwc(x).to(cuda))
     blob = G.tc_pack_up2(w.to(cuda)) if up else G.tc_pack(w.to(cuda))
@@ -159,6 +160,26 @@ def test_tc_cta_pair(cuda, B, H, W, Cin, Cout, kw):
     print(f"cta pair {B}x{H}x{W} {Cin}->{Cout} {kw}: rel err {e:.2e}, max |pair - single| {(y1 - y2).abs().max().item():.2e}")
     assert e <= 2e-5
     assert torch.equal(y1, y2), "same MMAs in the same order: the paired kernel must be bit-identical"
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 6, 128, 64, 64), (2, 5, 200, 64, 64), (1, 9, 384, 128, 128),
+                                           (1, 4, 130, 256, 128), (2, 7, 256, 128, 64)])
+def test_tc_strip_mode(cuda, B, H, W, Cin, Cout):
+    """Row-strip tiles: the three horizontal taps read one shared 130-pixel activation strip through descriptors
+    offset by kw rows (base-offset = swizzle phase)."""
+    x, w, b = rnd(B, Cin, H, W, seed=50), rnd(Cout, Cin, 3, 3, seed=51, scale=0.03), rnd(Cout, seed=52)
+    want = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    res = rnd(B, H, W, Cout, seed=53).to(cuda)
+    want = want + res.cpu().permute(0, 3, 1, 2).double()
+    hi, lo = G.tc_prepare(G.nhwc(x).to(cuda))
+    blob, bg = G.tc_pack(w.to(cuda)), b.to(cuda)
+    y0 = G.tc_igemm(hi, lo, blob, bg, Cout, 3, res1=res, strip=0, pair=0)
+    y1 = G.tc_igemm(hi, lo, blob, bg, Cout, 3, res1=res, strip=1)
+    e = rel_err(G.nchw(y1), want)
+    print(f"strip {B}x{H}x{W} {Cin}->{Cout}: rel err {e:.2e}, max |strip - per-tap| {(y0 - y1).abs().max().item():.2e}")
+    assert e <= 2e-5
+    # same products, different accumulation order (kh, chunk, kw instead of tap, chunk): equal up to accumulator rounding
+    assert (y0 - y1).abs().max().item() <= 1e-5 * y0.abs().max().item()
 
 
 def test_in_conv_split_planes(cuda):
