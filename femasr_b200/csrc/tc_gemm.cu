@@ -153,8 +153,8 @@ constexpr int A_PLANE_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 // L2->SM bottleneck of the short-K / narrow layers) is halved and one more pipeline stage fits.
 // STRIP = true (3x3 stride-1 convs on maps at least 128 wide, BN <= 128): the tile is one image row of 128 pixels
 // and the activation operand of the three horizontal taps (kw = 0,1,2) is ONE shared-memory strip of 130 pixels per
-// (kh, 64-channel chunk): tap kw reads it through a descriptor that starts kw rows (kw*128 B) into the strip, with the
-// descriptor's base-offset field carrying the swizzle phase.  Activation traffic from L2 drops 2.9x (3 loads
+// (kh, 64-channel chunk): tap kw reads it through a descriptor that simply starts kw rows (kw*128 B) into the strip
+// (the swizzle follows absolute address bits, see the MMA issuer).  Activation traffic from L2 drops 2.9x (3 loads
 // instead of 9 per chunk) - the narrow layers are L2->SM bound (profiles/tc_igemm_traffic_r1.json).  Weights stream
 // through their own ring, one tap per stage.
 constexpr int STRIP_PX = 130;                         // 128 outputs + one halo pixel each side
@@ -345,10 +345,12 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             mbar_wait(fullB_bar(sb), pb);
             tc_fence_after();
             const uint32_t b_base = smem_base + Cfg::SA_STAGES * Cfg::SA_BYTES + sb * Cfg::SB_BYTES;
-            // tap kw = the strip shifted by kw pixel rows; base-offset field (bits 49-51) = swizzle phase of the start row
-            const uint64_t shift = (uint64_t)kw << 49;
-            const uint64_t a_hi = make_sw128_desc(a_base + kw * 128) | shift;
-            const uint64_t a_lo = make_sw128_desc(a_base + STRIP_PLANE_BYTES + kw * 128) | shift;
+            // tap kw = the strip shifted by kw pixel rows.  Measured on B200: the tensor core derives the 128B-swizzle
+            // XOR from the absolute shared-memory address bits (like TMA does when it writes the strip), so a start
+            // address that is 128-byte but not 1024-byte aligned just works with base-offset 0; putting the row phase
+            // into the descriptor's base-offset field (bits 49-51) instead produces garbage.
+            const uint64_t a_hi = make_sw128_desc(a_base + kw * 128);
+            const uint64_t a_lo = make_sw128_desc(a_base + STRIP_PLANE_BYTES + kw * 128);
             const uint64_t b_hi = make_sw128_desc(b_base), b_lo = make_sw128_desc(b_base + Cfg::B_PLANE_BYTES);
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {

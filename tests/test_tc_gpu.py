@@ -166,7 +166,7 @@ def test_tc_cta_pair(cuda, B, H, W, Cin, Cout, kw):
                                            (1, 4, 130, 256, 128), (2, 7, 256, 128, 64)])
 def test_tc_strip_mode(cuda, B, H, W, Cin, Cout):
     """Row-strip tiles: the three horizontal taps read one shared 130-pixel activation strip through descriptors
-    offset by kw rows (base-offset = swizzle phase)."""
+    offset by kw rows."""
     x, w, b = rnd(B, Cin, H, W, seed=50), rnd(Cout, Cin, 3, 3, seed=51, scale=0.03), rnd(Cout, seed=52)
     want = F.conv2d(x.double(), w.double(), b.double(), padding=1)
     res = rnd(B, H, W, Cout, seed=53).to(cuda)
