@@ -14,7 +14,7 @@
 //   warp 1  MMA issuer (one elected thread): 4 k-steps x 3 split products per 64-wide k-block into a
 //           128 x BN fp32 accumulator in TMEM (two accumulators: the epilogue of tile i overlaps tile i+1).
 //   warp 2  TMEM allocator.
-//   warps 4-11 epilogue: tcgen05.ld 16 columns at a time -> *2^-s + bias -> GELU -> smem transpose ->
+//   warps 4-..  epilogue (4*NSPLIT warps): tcgen05.ld 16 columns at a time -> *2^-s + bias -> GELU -> smem transpose ->
 //           + prefetched residual(s) -> coalesced fp32 NHWC (or split-fp16 plane) stores.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -116,6 +116,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// (x, y) -> packed fp16 hi pair and lo pair; the conversion saturates to +-65504 instead of overflowing to inf
+__device__ __forceinline__ void split_pack2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y), "f"(x));     // d = {hi half: first src, lo half: second}
+  const __half2 h = *reinterpret_cast<const __half2*>(&hi);
+  const float2 hf = __half22float2(h);
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(y - hf.y), "f"(x - hf.x));
+}
+
 // K-major, 128B-swizzled operand tile ([rows][64 fp16], 8-row atoms of 1024 B): SBO = 1024 B, LBO unused (=1),
 // descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  cute::UMMA::SmemDescriptor bit layout.
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
@@ -146,6 +154,12 @@ struct TcP {
 };
 
 constexpr int TC_BM = 128, TC_BK = 64;
+#ifndef TC_NSPLIT
+#define TC_NSPLIT 2
+#endif
+constexpr int NSPLIT = TC_NSPLIT;                  // epilogue warps per TMEM lane quarter (column split): 2 or 4
+constexpr int EPI_WARPS = 4 * NSPLIT;
+constexpr int TC_THREADS = 128 + 32 * EPI_WARPS;
 constexpr int A_PLANE_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 
 // PAIR = true: two CTAs of a cluster (one TPC) cooperate on a 256 x BN tile with tcgen05 cta_group::2 - each
@@ -173,7 +187,7 @@ struct TcCfg {
   static constexpr int SB_STAGES = BN == 64 ? 6 : 4, SB_BYTES = 2 * B_PLANE_BYTES;
   static constexpr int PIPE_BYTES = STRIP ? SA_STAGES * SA_BYTES + SB_STAGES * SB_BYTES : STAGES * STAGE_BYTES;
   static constexpr int NBAR_PIPE = STRIP ? 2 * SA_STAGES + 2 * SB_STAGES : 2 * STAGES;   // full/empty barriers of the rings
-  static constexpr int EPI_BYTES = 8 * 2048 /*per-warp 32x16 fp32 transpose tiles*/ + 8 * 32 * 8 /*row offsets*/;
+  static constexpr int EPI_BYTES = EPI_WARPS * 2048 /*per-warp 32x16 fp32 transpose tiles*/;
   static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators; power of two for BN in {64,128,256}
   static_assert(8 * (NBAR_PIPE + 4) + 4 <= 256, "barrier area");
@@ -223,7 +237,7 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
 }
 
 template <int BN, bool PAIR, bool STRIP>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcP p) {
   using Cfg = TcCfg<BN, PAIR, STRIP>;
@@ -257,7 +271,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::NBAR_PIPE; ++s) mbar_init(bar_base + 8u * s, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), PAIR ? 512 : 256); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * 32 * EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (PAIR) cluster_sync_all(); else __syncthreads();
@@ -461,14 +475,14 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     // TMEM load / math of the current chunk (the stores may alias the residual, which otherwise pins every load
     // behind the previous store).
     const int e = warp - 4;
-    const int ew = e & 3, half = e >> 2;
+    const int ew = e & 3, part = e >> 2;             // TMEM lane quarter, column part
     const int row = ew * 32 + lane;
     const float inv_scale = __ldg(p.inv_scale);
     const uint32_t epi_base = bar_base + 256;
     float* stage = reinterpret_cast<float*>(smem_raw + (epi_base + (uint32_t)e * 2048u - smem_u32(smem_raw)));
-    long* rowoff = reinterpret_cast<long*>(smem_raw + (epi_base + 8u * 2048u - smem_u32(smem_raw))) + e * 32;
     const int q = lane & 3, rsub = lane >> 2;
-    constexpr int CH = 16, NCH = BN / 2 / CH;       // chunks per warp
+    constexpr int CW = BN / NSPLIT;                  // accumulator columns per warp
+    constexpr int CH = 16, NCH = CW / CH;            // chunks per warp
     int acc = 0; uint32_t acc_phase = 0;
     const bool sliced = p.slice_kb > 0;
     const int nslices = sliced ? (p.kb_end - p.kb_begin + p.slice_kb - 1) / p.slice_kb : 1;
@@ -483,25 +497,24 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       const bool valid = tc.real && y < p.H && x < p.W;
       const int oy = p.up ? 2 * y + (ph >> 1) : y, ox = p.up ? 2 * x + (ph & 1) : x;
       const int Ho = p.up ? 2 * p.H : p.H, Wo = p.up ? 2 * p.W : p.W;
-      const int col0 = nt * BN + half * (BN / 2);
-      rowoff[lane] = valid ? (((long)b * Ho + oy) * Wo + ox) * p.Cout + col0 : -1;
-      __syncwarp();
-      long offs[4];
+      const int col0 = nt * BN + part * CW;
+      const long myoff = valid ? (((long)b * Ho + oy) * Wo + ox) * p.Cout + col0 : -1;   // this lane's accumulator row
+      long offs[4];                                  // rows it*8 + rsub of the coalesced phase, columns 4q..4q+3
 #pragma unroll
-      for (int it = 0; it < 4; ++it) { const long o = rowoff[it * 8 + rsub]; offs[it] = o < 0 ? -1 : o + 4 * q; }
-      float4 cur[4], nxt[4];
+      for (int it = 0; it < 4; ++it) { const long o = __shfl_sync(0xffffffffu, myoff, it * 8 + rsub); offs[it] = o < 0 ? -1 : o + 4 * q; }
+      float4 cur[4];
       if (p.res1) {
 #pragma unroll
         for (int it = 0; it < 4; ++it)
           cur[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.res1 + offs[it]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       // sliced accumulation: fold all but the last partial into the running sum S (second TMEM buffer)
-      const uint32_t t_sum = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(BN + half * (BN / 2));
+      const uint32_t t_sum = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(BN + part * CW);
       for (int s = 0; s + 1 < nslices; ++s) {
         mbar_wait(tfull_bar(0), acc_phase);
         acc_phase ^= 1u;
         tc_fence_after();
-        const uint32_t t_part = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(half * (BN / 2));
+        const uint32_t t_part = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(part * CW);
 #pragma unroll 1
         for (int ci = 0; ci < NCH; ++ci) {
           uint32_t pr[16];
@@ -520,15 +533,10 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + part * CW);
 #pragma unroll 1
       for (int ci = 0; ci < NCH; ++ci) {
         const int c = ci * CH;
-        if (p.res1 && ci + 1 < NCH) {
-#pragma unroll
-          for (int it = 0; it < 4; ++it)
-            nxt[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.res1 + offs[it] + c + CH) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         uint32_t r[16];
         tmem_ld16(t_row + (uint32_t)c, r);
         if (nslices > 1) {
@@ -557,24 +565,26 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           if (offs[it] >= 0) {
             const long off = offs[it] + c;
             float4 o = *reinterpret_cast<const float4*>(&stage[rr * 16 + 4 * (q ^ ((rr >> 1) & 3))]);
-            if (p.res1) { o.x += cur[it].x; o.y += cur[it].y; o.z += cur[it].z; o.w += cur[it].w; }
+            if (p.res1) {
+              o.x += cur[it].x; o.y += cur[it].y; o.z += cur[it].z; o.w += cur[it].w;
+              // prefetch this row's residual for the next chunk into the same registers (latency overlaps the next
+              // chunk's TMEM load and row phase; the store below may alias res1 but never these columns)
+              if (ci + 1 < NCH) cur[it] = *reinterpret_cast<const float4*>(p.res1 + off + CH);
+            }
             if (p.res2) {
               const float4 rv = *reinterpret_cast<const float4*>(p.res2 + off);
               o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
             }
-            sa += o.x + o.y; ssa = fmaf(o.x, o.x, fmaf(o.y, o.y, ssa));
-            sb += o.z + o.w; ssb = fmaf(o.z, o.z, fmaf(o.w, o.w, ssb));
+            if (p.gn_partial) {
+              sa += o.x + o.y; ssa = fmaf(o.x, o.x, fmaf(o.y, o.y, ssa));
+              sb += o.z + o.w; ssb = fmaf(o.z, o.z, fmaf(o.w, o.w, ssb));
+            }
             if (p.out_hi) {
-              const float v[4] = {o.x, o.y, o.z, o.w};
-              __align__(8) __half h[4], l[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float cl = fminf(fmaxf(v[k], -65504.f), 65504.f);
-                h[k] = __float2half_rn(cl);
-                l[k] = __float2half_rn(cl - __half2float(h[k]));
-              }
-              *reinterpret_cast<uint2*>(p.out_hi + off) = *reinterpret_cast<const uint2*>(h);
-              *reinterpret_cast<uint2*>(p.out_lo + off) = *reinterpret_cast<const uint2*>(l);
+              uint2 h, l;
+              split_pack2(o.x, o.y, h.x, l.x);
+              split_pack2(o.z, o.w, h.y, l.y);
+              *reinterpret_cast<uint2*>(p.out_hi + off) = h;
+              *reinterpret_cast<uint2*>(p.out_lo + off) = l;
             } else {
               *reinterpret_cast<float4*>(p.y + off) = o;
             }
@@ -604,8 +614,6 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           }
         }
         __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
       }
       tc_fence_before();
       release_acc(acc);                         // 256 (512 when paired) arrivals release the accumulator
@@ -815,7 +823,7 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
   }
   if constexpr (!PAIR) {
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    tc_igemm_kernel<BN, false, STRIP><<<grid, 384, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
+    tc_igemm_kernel<BN, false, STRIP><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
     return launch_status("tc_igemm_kernel");
   } else {
     const int num_m = p.num_tiles / p.n_tiles;
@@ -823,7 +831,7 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
     const int work = phases * ((num_m / phases + 1) / 2) * p.n_tiles;
     const int pairs = work < sm_count() / 2 ? work : sm_count() / 2;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;

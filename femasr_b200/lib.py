@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfemasr_b200.so")
+LIB_PATH = os.environ.get("FEMASR_LIB") or os.path.join(_HERE, "libfemasr_b200.so")
 
 PRO_NONE, PRO_GN_SILU, PRO_LN = 0, 1, 2
 ACT_NONE, ACT_GELU = 0, 1
