@@ -141,7 +141,12 @@ class FeMaSRNet(nn.Module):
         if gt_indices is not None:
             raise NotImplementedError("gt_indices (training supervision branch) is outside the inference hot path")
         eng = self._native(input.device)
-        out, loss, idx = eng.forward(input)
+        if eng.use_graph and input.is_cuda:
+            # fixed launch list replayed as a CUDA graph; results are copied out of the graph's static buffers so the
+            # returned tensors stay valid across calls like the reference's
+            out, loss, idx = (t.clone() for t in eng.forward_graph(input))
+        else:
+            out, loss, idx = eng.forward(input)
         return out, loss, loss * 0, [idx]
 
     def decode_indices(self, indices):

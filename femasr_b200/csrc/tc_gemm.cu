@@ -184,13 +184,17 @@ struct TcCfg {
   static constexpr int STAGES = PAIR ? (BN == 256 ? 3 : 4) : (BN == 256 ? 2 : (BN == 128 ? 3 : 4));
   // separate rings (strip)
   static constexpr int SA_STAGES = 2, SA_BYTES = 2 * STRIP_PLANE_BYTES;
-  static constexpr int SB_STAGES = BN == 64 ? 6 : 4, SB_BYTES = 2 * B_PLANE_BYTES;
+  static constexpr int SB_BYTES = 2 * B_PLANE_BYTES;
+  static constexpr int SB_BUDGET = 232448 - 1024 - 256 - EPI_WARPS * 2048 - SA_STAGES * SA_BYTES;   // what is left of 227 KB
+  static constexpr int SB_STAGES = SB_BUDGET / SB_BYTES > 6 ? 6 : SB_BUDGET / SB_BYTES;
   static constexpr int PIPE_BYTES = STRIP ? SA_STAGES * SA_BYTES + SB_STAGES * SB_BYTES : STAGES * STAGE_BYTES;
   static constexpr int NBAR_PIPE = STRIP ? 2 * SA_STAGES + 2 * SB_STAGES : 2 * STAGES;   // full/empty barriers of the rings
   static constexpr int EPI_BYTES = EPI_WARPS * 2048 /*per-warp 32x16 fp32 transpose tiles*/;
   static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators; power of two for BN in {64,128,256}
   static_assert(8 * (NBAR_PIPE + 4) + 4 <= 256, "barrier area");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(!STRIP || SB_STAGES >= 2, "strip weight ring too small");
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {

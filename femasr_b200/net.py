@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -60,6 +61,9 @@ class NativeNet:
         self.device: Optional[torch.device] = None
         self.names = [n for (n, _s, kind, _f) in param_spec(self.scale, self.e_dim, self.n_e)
                       if kind not in ("rpi", "mask")]
+        # the forward is a fixed launch list per input shape: replay it as a CUDA graph (no per-launch host work)
+        self.use_graph = os.environ.get("FEMASR_CUDA_GRAPH", "1") != "0"
+        self._graphs: Dict[Tuple[int, int, int], dict] = {}
 
     # ------------------------------------------------------------------ lifecycle
     def _ensure(self, device: torch.device):
@@ -87,6 +91,7 @@ class NativeNet:
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor], device: torch.device):
         """Upload every float parameter by its reference name (engine keeps repacked device copies)."""
+        self._graphs.clear()           # captured graphs hold the old weight pointers' contents only by address: re-capture
         device = torch.device(device)
         if device.type == "cuda" and device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
@@ -152,6 +157,33 @@ class NativeNet:
         if taps:
             return y, loss, idx, tap_out
         return y, loss, idx
+
+    def forward_graph(self, x: torch.Tensor):
+        """encode_and_decode through a captured CUDA graph (one per input shape).  Returns (y, loss, idx) living in
+        the graph's static output buffers: valid until the next call with the same shape (clone to keep)."""
+        self._ensure(x.device)
+        x = x.detach().float().contiguous()
+        key = tuple(x.shape)
+        ent = self._graphs.get(key)
+        if ent is None:
+            with torch.cuda.device(self.device):
+                xs = torch.empty_like(x)
+                xs.copy_(x)
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self.forward(xs)                      # warm-up: one-time attribute/workspace set-up happens here
+                    side.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        y, loss, idx = self.forward(xs)
+                torch.cuda.current_stream().wait_stream(side)
+                ent = {"graph": g, "x": xs, "y": y, "loss": loss, "idx": idx, "ws": self._ws}
+                self._ws = None                           # the captured launches own this workspace from now on
+                self._graphs[key] = ent
+        ent["x"].copy_(x, non_blocking=True)
+        ent["graph"].replay()
+        return ent["y"], ent["loss"], ent["idx"]
 
     def tap_shapes(self, B: int, H: int, W: int) -> Dict[str, Tuple[int, ...]]:
         s = self.scale
