@@ -29,6 +29,7 @@ struct Arena {
   char* base = nullptr;
   size_t top = 0, peak = 0, cap = 0;
   bool dry = true;
+  bool overflow = false;      // real run only: an allocation ran past the caller's workspace (sizing bug) - never launch on it
   static size_t align(size_t n) { return (n + 255) & ~size_t(255); }
   size_t alloc_off(size_t bytes) {
     bytes = align(std::max<size_t>(bytes, 256));
@@ -47,6 +48,7 @@ struct Arena {
     blks.push_back(b);
     top += bytes;
     peak = std::max(peak, top);
+    if (!dry && top > cap) overflow = true;
     return b.off;
   }
   float* alloc(size_t nfloats) {
@@ -192,6 +194,7 @@ struct Ctx {
   template <class F>
   void run(const char* name, double flops, F&& f) {
     if (dry() || !ok()) return;
+    if (ar.overflow) { check(fail(FEMASR_ERR_STATE, "workspace plan mismatch: the graph needs more than femasr_net_workspace_bytes reported")); return; }
     if (net->profile) {
       ProfRec r{name, flops, nullptr, nullptr};
       cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
@@ -470,12 +473,11 @@ struct Ctx {
     precise_region = true;
     const float *iw = P(enc + ".in_conv.weight"), *ib = P(enc + ".in_conv.bias");
     const double in_flops = 2.0 * 16 * cfg.in_channel * c * (double)B * h * w;
-    const bool want_in_tap = !dry() && net->taps.count("in_conv") && net->taps["in_conv"].dst;
+    const bool want_in_tap = net->taps.count("in_conv") && net->taps["in_conv"].dst;
     float* cur = nullptr;                 // fp32 in_conv output (SIMT path, or when its tap is requested)
     float* in_hi = nullptr; float* in_lo = nullptr;   // tensor-core path: in_conv writes the split operand planes directly
     const size_t in_elems = (size_t)B * h * w * c;
-    if (!tc || want_in_tap || dry()) {
-      // (dry runs always reserve it so the workspace also covers a later tap request)
+    if (!tc || want_in_tap) {     // identical in the dry (sizing) run and the real run: taps are registered first
       cur = ar.alloc(in_elems);
       const int c0 = c;
       if (!tc || want_in_tap)
@@ -711,7 +713,7 @@ extern "C" int femasr_net_decode_indices(femasr_net* net, const int64_t* indices
   if (workspace_bytes < need) return fail(FEMASR_ERR_STATE, "decode_indices: workspace too small");
   const uintptr_t mis = (256 - ((uintptr_t)workspace & 255)) & 255;
   Ctx c; c.net = net; c.st = as_stream(stream); c.ar.dry = false;
-  c.ar.base = reinterpret_cast<char*>(workspace) + mis;
+  c.ar.base = reinterpret_cast<char*>(workspace) + mis; c.ar.cap = workspace_bytes - mis;
   const long l0 = g_launches;
   c.decode_indices(indices, y, B, h, w);
   net->last_launches = (int)(g_launches - l0);

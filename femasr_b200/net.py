@@ -133,9 +133,6 @@ class NativeNet:
         B, _, H, W = x.shape
         s = self.scale
         with torch.cuda.device(self.device):
-            need = C.c_size_t()
-            L.check(self.lib.femasr_net_workspace_bytes(self._h, B, H, W, C.byref(need)))
-            ws = self._workspace(need.value)
             y = torch.empty((B, 3, H * s, W * s), dtype=torch.float32, device=self.device)
             div = 2 if s == 4 else 4
             h, w = H // div, W // div
@@ -148,6 +145,10 @@ class NativeNet:
                     t = torch.empty(shapes[name], dtype=torch.float32, device=self.device)
                     tap_out[name] = t
                     L.check(self.lib.femasr_net_set_tap(self._h, name.encode(), t.data_ptr(), t.numel()))
+            # sized AFTER the taps are registered: the engine's plan (and so its workspace) depends on them
+            need = C.c_size_t()
+            L.check(self.lib.femasr_net_workspace_bytes(self._h, B, H, W, C.byref(need)))
+            ws = self._workspace(need.value)
             try:
                 L.check(self.lib.femasr_net_forward(self._h, x.data_ptr(), y.data_ptr(), _ptr(idx), _ptr(loss),
                                                     B, H, W, ws.data_ptr(), ws.numel(), _stream()))
