@@ -506,7 +506,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       long offs[4];                                  // rows it*8 + rsub of the coalesced phase, columns 4q..4q+3
 #pragma unroll
       for (int it = 0; it < 4; ++it) { const long o = __shfl_sync(0xffffffffu, myoff, it * 8 + rsub); offs[it] = o < 0 ? -1 : o + 4 * q; }
-      float4 cur[4];
+      float4 cur[4], nxt[4];
       if (p.res1) {
 #pragma unroll
         for (int it = 0; it < 4; ++it)
@@ -541,6 +541,12 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll 1
       for (int ci = 0; ci < NCH; ++ci) {
         const int c = ci * CH;
+        if (p.res1 && ci + 1 < NCH) {
+          // next chunk's residual, requested a whole chunk ahead (DRAM latency ~ one chunk of epilogue work)
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            nxt[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.res1 + offs[it] + c + CH) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         uint32_t r[16];
         tmem_ld16(t_row + (uint32_t)c, r);
         if (nslices > 1) {
@@ -569,12 +575,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           if (offs[it] >= 0) {
             const long off = offs[it] + c;
             float4 o = *reinterpret_cast<const float4*>(&stage[rr * 16 + 4 * (q ^ ((rr >> 1) & 3))]);
-            if (p.res1) {
-              o.x += cur[it].x; o.y += cur[it].y; o.z += cur[it].z; o.w += cur[it].w;
-              // prefetch this row's residual for the next chunk into the same registers (latency overlaps the next
-              // chunk's TMEM load and row phase; the store below may alias res1 but never these columns)
-              if (ci + 1 < NCH) cur[it] = *reinterpret_cast<const float4*>(p.res1 + off + CH);
-            }
+            if (p.res1) { o.x += cur[it].x; o.y += cur[it].y; o.z += cur[it].z; o.w += cur[it].w; }
             if (p.res2) {
               const float4 rv = *reinterpret_cast<const float4*>(p.res2 + off);
               o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
@@ -618,6 +619,8 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           }
         }
         __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
       }
       tc_fence_before();
       release_acc(acc);                         // 256 (512 when paired) arrivals release the accumulator
