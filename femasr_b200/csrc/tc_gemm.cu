@@ -7,14 +7,14 @@
 // i.e. ~22 significand bits per operand; the dropped a_lo*w_lo term is ~2^-22 relative (SURVEY 7.3-1:
 // the path needs >=18 bits before the VQ and >=13 after it; single-pass fp16/bf16/tf32 fails parity).
 //
-// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
+// Structure (one persistent CTA per SM, 640 threads, warp-specialised):
 //   warp 0  TMA producer: activation tile = 4-D box (64 ch x Wt x Ht x 1) of the NHWC fp16 planes at the
 //           tap offset (kh-1, kw-1) - out-of-bounds rows/cols are zero-filled by TMA, which IS the conv
 //           padding - and the weight tile = 2-D box (64 x BN) of the K-major fp16 planes; 128B swizzle.
 //   warp 1  MMA issuer (one elected thread): 4 k-steps x 3 split products per 64-wide k-block into a
 //           128 x BN fp32 accumulator in TMEM (two accumulators: the epilogue of tile i overlaps tile i+1).
 //   warp 2  TMEM allocator.
-//   warps 4-..  epilogue (4*NSPLIT warps): tcgen05.ld 16 columns at a time -> *2^-s + bias -> GELU -> smem transpose ->
+//   warps 4-19 epilogue (4*NSPLIT = 16 warps; 8 measured 4 % slower on the short-K layers): tcgen05.ld 16 columns at a time -> *2^-s + bias -> GELU -> smem transpose ->
 //           + prefetched residual(s) -> coalesced fp32 NHWC (or split-fp16 plane) stores.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -155,7 +155,7 @@ struct TcP {
 
 constexpr int TC_BM = 128, TC_BK = 64;
 #ifndef TC_NSPLIT
-#define TC_NSPLIT 2
+#define TC_NSPLIT 4
 #endif
 constexpr int NSPLIT = TC_NSPLIT;                  // epilogue warps per TMEM lane quarter (column split): 2 or 4
 constexpr int EPI_WARPS = 4 * NSPLIT;
