@@ -14,7 +14,7 @@
 //   warp 1  MMA issuer (one elected thread): 4 k-steps x 3 split products per 64-wide k-block into a
 //           128 x BN fp32 accumulator in TMEM (two accumulators: the epilogue of tile i overlaps tile i+1).
 //   warp 2  TMEM allocator.
-//   warps 4-19 epilogue (4*NSPLIT = 16 warps; 8 measured 4 % slower on the short-K layers): tcgen05.ld 16 columns at a time -> *2^-s + bias -> GELU -> smem transpose ->
+//   warps 4-19 epilogue (16 warps; 8 for the 64-wide tiles): tcgen05.ld 16 columns at a time -> *2^-s + bias -> GELU -> smem transpose ->
 //           + prefetched residual(s) -> coalesced fp32 NHWC (or split-fp16 plane) stores.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -154,12 +154,11 @@ struct TcP {
 };
 
 constexpr int TC_BM = 128, TC_BK = 64;
-#ifndef TC_NSPLIT
-#define TC_NSPLIT 4
-#endif
-constexpr int NSPLIT = TC_NSPLIT;                  // epilogue warps per TMEM lane quarter (column split): 2 or 4
-constexpr int EPI_WARPS = 4 * NSPLIT;
-constexpr int TC_THREADS = 128 + 32 * EPI_WARPS;
+// epilogue warps per TMEM lane quarter (= column split of the accumulator): 4 (16 epilogue warps) for the 128/256-wide
+// tiles - measured +4 % end to end over 8 warps, the short-K layers are epilogue-issue bound - but 2 for the 64-wide
+// tiles, where a warp would own a single 16-column chunk and the per-tile fixed work dominates (measured -15 %).
+constexpr int nsplit_for(int BN) { return BN == 64 ? 2 : 4; }
+constexpr int tc_threads_for(int BN) { return 128 + 32 * 4 * nsplit_for(BN); }
 constexpr int A_PLANE_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 
 // PAIR = true: two CTAs of a cluster (one TPC) cooperate on a 256 x BN tile with tcgen05 cta_group::2 - each
@@ -185,6 +184,7 @@ struct TcCfg {
   // separate rings (strip)
   static constexpr int SA_STAGES = 2, SA_BYTES = 2 * STRIP_PLANE_BYTES;
   static constexpr int SB_BYTES = 2 * B_PLANE_BYTES;
+  static constexpr int NSPLIT = nsplit_for(BN), EPI_WARPS = 4 * NSPLIT, THREADS = tc_threads_for(BN);
   static constexpr int SB_BUDGET = 232448 - 1024 - 256 - EPI_WARPS * 2048 - SA_STAGES * SA_BYTES;   // what is left of 227 KB
   static constexpr int SB_STAGES = SB_BUDGET / SB_BYTES > 6 ? 6 : SB_BUDGET / SB_BYTES;
   static constexpr int PIPE_BYTES = STRIP ? SA_STAGES * SA_BYTES + SB_STAGES * SB_BYTES : STAGES * STAGE_BYTES;
@@ -241,7 +241,7 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
 }
 
 template <int BN, bool PAIR, bool STRIP>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads_for(BN), 1)
 tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcP p) {
   using Cfg = TcCfg<BN, PAIR, STRIP>;
@@ -275,7 +275,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::NBAR_PIPE; ++s) mbar_init(bar_base + 8u * s, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * 32 * EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * 32 * Cfg::EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (PAIR) cluster_sync_all(); else __syncthreads();
@@ -485,7 +485,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const uint32_t epi_base = bar_base + 256;
     float* stage = reinterpret_cast<float*>(smem_raw + (epi_base + (uint32_t)e * 2048u - smem_u32(smem_raw)));
     const int q = lane & 3, rsub = lane >> 2;
-    constexpr int CW = BN / NSPLIT;                  // accumulator columns per warp
+    constexpr int CW = BN / Cfg::NSPLIT;             // accumulator columns per warp
     constexpr int CH = 16, NCH = CW / CH;            // chunks per warp
     int acc = 0; uint32_t acc_phase = 0;
     const bool sliced = p.slice_kb > 0;
@@ -830,7 +830,7 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
   }
   if constexpr (!PAIR) {
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    tc_igemm_kernel<BN, false, STRIP><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
+    tc_igemm_kernel<BN, false, STRIP><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
     return launch_status("tc_igemm_kernel");
   } else {
     const int num_m = p.num_tiles / p.n_tiles;
@@ -838,7 +838,7 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
     const int work = phases * ((num_m / phases + 1) / 2) * p.n_tiles;
     const int pairs = work < sm_count() / 2 ? work : sm_count() / 2;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
