@@ -164,6 +164,12 @@ class FeMaSRNet(nn.Module):
         """femasr_arch.py:449-468."""
         return self._native(input.device).test(input)
 
+    @torch.no_grad()
+    def sr_uint8(self, images):
+        """Extension (not in the reference): uint8 BGR HWC batch in, uint8 BGR HWC batch out, boundary fused on
+        the device - img2tensor, /255, test() padding and crop, tensor2img (inference_femasr.py:54-64)."""
+        return self._native(images.device).sr_uint8(images)
+
     def forward(self, input, gt_indices=None):
         """femasr_arch.py:470-479."""
         return self.encode_and_decode(input, gt_indices)

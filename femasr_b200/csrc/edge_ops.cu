@@ -173,6 +173,31 @@ __global__ void flip_pad_kernel(const float* __restrict__ x, float* __restrict__
   y[i] = x[(bc * h + sr) * w + sj];
 }
 
+// uint8 image boundary (inference_femasr.py:54-56,64 + basicsr/utils/img_util.py:9-35,38-94):
+//   in : uint8 HWC BGR [B,h,w,3]  -> fp32 NCHW RGB /255, flip-padded to [B,3,hp,wp]  (img2tensor, /255., test() padding)
+//   out: fp32 NCHW RGB [B,3,SH,SW] -> clamp to [0,1], *255, round-half-even, uint8 HWC BGR, cropped to [B,ch,cw,3]
+__global__ void u8_to_input_kernel(const uint8_t* __restrict__ img, float* __restrict__ x, int h, int w, int hp, int wp, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;     // index into [B,3,hp,wp]
+  if (i >= n) return;
+  const int j = (int)(i % wp);
+  const int r = (int)((i / wp) % hp);
+  const int c = (int)((i / wp / hp) % 3);
+  const long b = i / wp / hp / 3;
+  const int sr = r < h ? r : 2 * h - 1 - r, sj = j < w ? j : 2 * w - 1 - j;
+  x[i] = (float)img[((b * h + sr) * w + sj) * 3 + (2 - c)] / 255.0f;   // torch: float32(img) / 255.
+}
+__global__ void output_to_u8_kernel(const float* __restrict__ y, uint8_t* __restrict__ img, int SH, int SW, int ch, int cw, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;     // index into [B,ch,cw,3]
+  if (i >= n) return;
+  const int c = (int)(i % 3);
+  const int j = (int)((i / 3) % cw);
+  const int r = (int)((i / 3 / cw) % ch);
+  const long b = i / 3 / cw / ch;
+  float v = y[((b * 3 + (2 - c)) * SH + r) * SW + j];
+  v = fminf(fmaxf(v, 0.0f), 1.0f);
+  img[i] = (uint8_t)rintf(v * 255.0f);                              // numpy round(): half to even
+}
+
 __global__ void copy_window_kernel(const float* __restrict__ src, float* __restrict__ dst, int sh, int sw, int dh, int dw,
                                    int sy, int sx, int dy, int dx, int ch, int cw, long n) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,6 +287,21 @@ extern "C" int femasr_flip_pad(const float* x, float* y, int B, int C, int h, in
   const long n = (long)B * C * hp * wp;
   flip_pad_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(x, y, h, w, hp, wp, n);
   return launch_status("flip_pad_kernel");
+}
+
+extern "C" int femasr_u8_to_input(const uint8_t* bgr_hwc, float* x_nchw, int B, int h, int w, int hp, int wp, void* stream) {
+  FEMASR_CHECK_ARG(bgr_hwc && x_nchw && B > 0 && h > 0 && w > 0, "u8_to_input: bad argument");
+  FEMASR_CHECK_ARG(hp >= h && wp >= w && hp <= 2 * h && wp <= 2 * w, "u8_to_input: pad must be within one reflection");
+  const long n = (long)B * 3 * hp * wp;
+  u8_to_input_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(bgr_hwc, x_nchw, h, w, hp, wp, n);
+  return launch_status("u8_to_input_kernel");
+}
+
+extern "C" int femasr_output_to_u8(const float* y_nchw, uint8_t* bgr_hwc, int B, int SH, int SW, int ch, int cw, void* stream) {
+  FEMASR_CHECK_ARG(y_nchw && bgr_hwc && B > 0 && ch > 0 && cw > 0 && ch <= SH && cw <= SW, "output_to_u8: bad argument");
+  const long n = (long)B * ch * cw * 3;
+  output_to_u8_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(y_nchw, bgr_hwc, SH, SW, ch, cw, n);
+  return launch_status("output_to_u8_kernel");
 }
 
 extern "C" int femasr_copy_window(const float* src, float* dst, int B, int C, int sh, int sw, int dh, int dw, int sy,

@@ -70,6 +70,8 @@ SIGNATURES = {
     "femasr_net_profile_json": (C.c_char_p, [_V]),
     "femasr_net_flops": (_D, [_V, _I, _I, _I]),
     "femasr_flip_pad": (_I, [_V, _V, _I, _I, _I, _I, _I, _I, _V]),
+    "femasr_u8_to_input": (_I, [_V, _V, _I, _I, _I, _I, _I, _V]),
+    "femasr_output_to_u8": (_I, [_V, _V, _I, _I, _I, _I, _I, _V]),
     "femasr_copy_window": (_I, [_V, _V] + [_I] * 12 + [_V]),
     "femasr_pack_weight": (_I, [_V, _V, _I, _I, _I, _I, _V]),
     "femasr_igemm_simt": (_I, [C.POINTER(IgemmArgs), _V]),

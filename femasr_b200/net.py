@@ -241,6 +241,26 @@ class NativeNet:
                                                 0, 0, 0, 0, h * s, w * s, _stream()))
         return y
 
+    def sr_uint8(self, images: torch.Tensor) -> torch.Tensor:
+        """Whole-image SR with the uint8 boundary on the device: images uint8 [B,h,w,3] BGR (what cv2.imread
+        returns, stacked) on the GPU -> uint8 [B,s*h,s*w,3] BGR.  Equals tensor2img(test(img2tensor(img)/255.))
+        of the reference's inference loop (inference_femasr.py:54-64) for same-shape images, with one quarter of
+        the device->host bytes and no host-side float image math."""
+        if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[3] != 3:
+            raise L.FemasrError(f"expected uint8 [B,h,w,3], got {images.dtype} {tuple(images.shape)}")
+        self._ensure(images.device)
+        images = images.contiguous()
+        B, h, w, _ = images.shape
+        s = self.scale
+        hp, wp = padded_size(h, s), padded_size(w, s)
+        with torch.cuda.device(self.device):
+            xp = torch.empty((B, 3, hp, wp), dtype=torch.float32, device=self.device)
+            L.check(self.lib.femasr_u8_to_input(images.data_ptr(), xp.data_ptr(), B, h, w, hp, wp, _stream()))
+            yp = (self.forward_graph(xp) if self.use_graph else self.forward(xp, want_indices=False, want_loss=False))[0]
+            out = torch.empty((B, h * s, w * s, 3), dtype=torch.uint8, device=self.device)
+            L.check(self.lib.femasr_output_to_u8(yp.data_ptr(), out.data_ptr(), B, hp * s, wp * s, h * s, w * s, _stream()))
+        return out
+
     def test_tile(self, x: torch.Tensor, tile_size: int = 240, tile_pad: int = 16,
                   max_batch: int = 64) -> torch.Tensor:
         """femasr_arch.py:387-447.  Tiles are independent (every op on the path is per-sample), so

@@ -101,6 +101,14 @@ int femasr_flip_pad(const float* x, float* y, int B, int C, int h, int w, int hp
 int femasr_copy_window(const float* src, float* dst, int B, int C, int sh, int sw, int dh, int dw,
                        int sy, int sx, int dy, int dx, int ch, int cw, void* stream);
 
+/* uint8 image boundary fused on the device (inference_femasr.py:54-56,64; utils/img_util.py:9-35,38-94):
+ *   femasr_u8_to_input:  uint8 HWC BGR [B,h,w,3] -> fp32 NCHW RGB in [0,1], flip-padded to [B,3,hp,wp]
+ *                        (= img2tensor, /255., and test()'s padding in one pass)
+ *   femasr_output_to_u8: fp32 NCHW RGB [B,3,SH,SW] -> uint8 HWC BGR [B,ch,cw,3] of the top-left ch x cw crop
+ *                        (= test()'s crop and tensor2img: clamp to [0,1], *255, round half to even) */
+int femasr_u8_to_input(const uint8_t* bgr_hwc, float* x_nchw, int B, int h, int w, int hp, int wp, void* stream);
+int femasr_output_to_u8(const float* y_nchw, uint8_t* bgr_hwc, int B, int SH, int SW, int ch, int cw, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Operator-level API (what the network is built from; exported so each kernel has its own parity
  * test).  All tensors device fp32 unless stated.

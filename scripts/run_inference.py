@@ -32,6 +32,9 @@ def main(argv=None):
     ap.add_argument("--suffix", default="")
     ap.add_argument("--max_size", type=int, default=600)
     ap.add_argument("--e_dim", type=int, default=512, help="codebook dim (released weights: 512)")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="extension: >0 buckets same-shape images and super-resolves them N at a time with the uint8 "
+                         "image boundary fused on the device (FeMaSRNet.sr_uint8); 0 = the reference's one-by-one loop")
     a = ap.parse_args(argv)
     dev = torch.device("cuda" if torch.cuda.is_available() else "cpu")
     wpath = a.weight or load_file_from_url(URLS[a.out_scale])
@@ -40,13 +43,34 @@ def main(argv=None):
     net.eval()
     os.makedirs(a.output, exist_ok=True)
     paths = [a.input] if os.path.isfile(a.input) else sorted(glob.glob(os.path.join(a.input, "*")))
+
+    def save(path, img):
+        name, ext = os.path.splitext(os.path.basename(path))
+        imwrite(img, os.path.join(a.output, f"{name}{a.suffix}{ext}"))
+
+    if a.batch > 0 and dev.type == "cuda":
+        buckets, rest = {}, []
+        for path in paths:
+            img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+            if img is not None and img.ndim == 3 and img.shape[2] == 3 and img.dtype == "uint8" and \
+                    img.shape[0] * img.shape[1] < a.max_size ** 2:
+                buckets.setdefault(img.shape[:2], []).append((path, img))
+            else:
+                rest.append(path)
+        for items in buckets.values():
+            for i in range(0, len(items), a.batch):
+                chunk = items[i:i + a.batch]
+                batch = torch.from_numpy(__import__("numpy").stack([im for _, im in chunk])).to(dev)
+                out = net.sr_uint8(batch).cpu().numpy()
+                for (path, _), o in zip(chunk, out):
+                    save(path, o)
+        paths = rest
     for path in paths:
         img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
         x = (img2tensor(img).to(dev) / 255.0).unsqueeze(0)
         h, w = x.shape[2:]
         out = net.test(x) if h * w < a.max_size ** 2 else net.test_tile(x)
-        name, ext = os.path.splitext(os.path.basename(path))
-        imwrite(tensor2img(out), os.path.join(a.output, f"{name}{a.suffix}{ext}"))
+        save(path, tensor2img(out))
     return 0
 
 

@@ -77,3 +77,33 @@ def test_demo_entry_matches_oracle_pngs(tmp_path, cuda):
         assert got.shape == want_img.shape == (img.shape[0] * 4, img.shape[1] * 4, 3)
         diff = np.abs(got.astype(int) - want_img.astype(int))
         assert diff.max() <= 1 and (diff > 0).mean() < 0.01, "PNG outputs must match to +-1 LSB"
+    # bucketed uint8 fast path writes the same files
+    out2 = tmp_path / "out2"
+    assert run_inference.main(["-s", "4", "-i", str(tmp_path / "in"), "-o", str(out2), "-w", str(w), "--max_size", "70",
+                               "--batch", "4"]) == 0
+    for p in ins:
+        a = cv2.imread(str(out_dir / os.path.basename(p)), cv2.IMREAD_UNCHANGED)
+        b = cv2.imread(str(out2 / os.path.basename(p)), cv2.IMREAD_UNCHANGED)
+        d = np.abs(a.astype(int) - b.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3
+
+
+@pytest.mark.gpu
+def test_uint8_boundary_matches_reference_image_pipeline(cuda):
+    """sr_uint8 == tensor2img(test(img2tensor(img)/255)) of the reference's loop, bit for bit in uint8 except where
+    the fp32 value sits within rounding noise of a .5 boundary."""
+    from basicsr.archs.femasr_arch import FeMaSRNet
+    sd = random_state_dict(4, 256, seed=4, init="perturbed")
+    net = FeMaSRNet(codebook_params=[[32, 1024, 256]], LQ_stage=True, scale_factor=4)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda).eval()
+    rng = np.random.default_rng(5)
+    imgs = rng.integers(0, 256, (3, 40, 24, 3), dtype=np.uint8)
+    got = net.sr_uint8(torch.from_numpy(imgs).to(cuda)).cpu().numpy()
+    assert got.shape == (3, 160, 96, 3) and got.dtype == np.uint8
+    for k in range(3):
+        x = (img2tensor(imgs[k]) / 255.0).unsqueeze(0)
+        want_f = net.test(x.to(cuda))
+        want = tensor2img(want_f)
+        diff = np.abs(got[k].astype(int) - want.astype(int))
+        assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
