@@ -7,8 +7,9 @@ and return tuples.  The module only HOLDS the parameters (so `.to()`, `.eval()`,
 decode_indices runs in libfemasr_b200.so (hand-written sm_100a CUDA) through `femasr_b200.net`.
 There is no CPU or eager-PyTorch fallback: calling the network without a CUDA sm_100 device raises.
 
-In scope: LQ_stage=True, norm_type 'gn', act_type 'silu', one codebook at scale 32,
-scale_factor 2 or 4, inference (no autograd through the engine).  Anything else raises
+In scope: norm_type 'gn', act_type 'silu', one codebook at scale 32; LQ_stage=True with scale_factor 2 or 4 (the SR
+network) and LQ_stage=False (the HQ autoencoder that produces gt_indices / codebook visualisations); inference only
+(no autograd through the engine).  Anything else raises
 NotImplementedError at construction instead of silently computing something different.
 """
 from __future__ import annotations
@@ -71,14 +72,12 @@ class FeMaSRNet(nn.Module):
         if cb.ndim != 2 or cb.shape[1] != 3:
             raise ValueError("codebook_params must be [[scale, n_e, e_dim], ...]")
         unsupported = []
-        if not LQ_stage:
-            unsupported.append("LQ_stage=False (HQ autoencoder stage)")
         if cb.shape[0] != 1 or int(cb[0, 0]) != 32:
             unsupported.append("multi-scale codebooks / codebook scale != 32")
         if norm_type != 'gn' or act_type != 'silu':
             unsupported.append(f"norm_type={norm_type!r}/act_type={act_type!r}")
-        if scale_factor not in (2, 4) or gt_resolution != 256 or in_channel != 3:
-            unsupported.append("scale_factor not in {2,4} / gt_resolution != 256 / in_channel != 3")
+        if (LQ_stage and scale_factor not in (2, 4)) or gt_resolution != 256 or in_channel != 3:
+            unsupported.append("LQ-stage scale_factor not in {2,4} / gt_resolution != 256 / in_channel != 3")
         if use_semantic_loss:
             unsupported.append("use_semantic_loss=True (training-only VGG branch)")
         if unsupported:
@@ -90,13 +89,13 @@ class FeMaSRNet(nn.Module):
         self.in_channel = in_channel
         self.gt_res = gt_resolution
         self.LQ_stage = LQ_stage
-        self.scale_factor = scale_factor
+        self.scale_factor = scale_factor if LQ_stage else 1      # femasr_arch.py:241
         self.use_residual = use_residual
         self.use_semantic_loss = False
         self.max_depth = int(np.log2(gt_resolution // self.codebook_scale[0]))
         self.gemm_path = int(ignore_kwargs.get("gemm_path", -1))    # -1: engine default
 
-        for name, shape, kind, fan_in in param_spec(scale_factor, self.e_dim, self.n_e, in_channel):
+        for name, shape, kind, fan_in in param_spec(self.scale_factor, self.e_dim, self.n_e, in_channel):
             if kind == "rpi":
                 _attach(self, name, relative_position_index(), buffer=True)
             elif kind == "mask":

@@ -90,7 +90,8 @@ using namespace femasr;
 
 struct femasr_net {
   femasr_net_config cfg;
-  int depth;   // encode depth (1 for x4, 2 for x2)
+  int depth;   // encode depth (1 for x4, 2 for x2, 3 for the HQ autoencoder)
+  bool hq = false;   // scale_factor 1: LQ_stage=False graph (no Swin, no up branches, no skip adds)
   std::map<std::string, ParamInfo> spec;
   std::map<std::string, DevBuf> raw;      // fp32 copy in the reference layout
   std::map<std::string, DevBuf> packed;   // K-major GEMM operand / expanded rel bias / codebook^T
@@ -146,7 +147,7 @@ static void build_spec(femasr_net* n) {
     res /= 2;
   }
   const std::string sw = enc + ".blocks." + std::to_string(d) + ".swin_blks.";
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < (n->hq ? 0 : 4); ++r) {
     for (int b = 0; b < 6; ++b) {
       const std::string p = sw + std::to_string(r) + ".residual_group.blocks." + std::to_string(b);
       add_vec(n, p + ".norm1.weight", 256); add_vec(n, p + ".norm1.bias", 256);
@@ -159,7 +160,7 @@ static void build_spec(femasr_net* n) {
     }
     add_conv(n, sw + std::to_string(r) + ".conv", 256, 256, 3);
   }
-  for (int j = d + 1; j <= d + 2; ++j) {
+  for (int j = d + 1; j <= (n->hq ? d : d + 2); ++j) {
     const std::string b = enc + ".blocks." + std::to_string(j);
     add_conv(n, b + ".1", chan(res), chan(res * 2), 3);
     add_resblock(n, b + ".2", chan(res * 2));
@@ -492,7 +493,7 @@ struct Ctx {
     }
     for (int i = 0; i < d; ++i) {
       const std::string b = enc + ".blocks." + std::to_string(i);
-      const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1, co = 256;
+      const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1, co = chan((256 / cfg.scale_factor) >> (i + 1));
       float* nxt = ar.alloc((size_t)B * ho * wo * co);
       Stats sd0;
       if (tc) {
@@ -509,11 +510,11 @@ struct Ctx {
       resblock(b + ".2", cur, B, h, w, c, nullptr, sd, false);
     }
     tap("down", cur, (size_t)B * h * w * c);
-    swin(enc + ".blocks." + std::to_string(d), cur, B, h, w);
+    if (!net->hq) swin(enc + ".blocks." + std::to_string(d), cur, B, h, w);
     tap("swin", cur, (size_t)B * h * w * c);
     float *u1 = nullptr, *u2 = nullptr;
     precise_region = false;        // the up branches only reach the decoder's skip adds (femasr_arch.py:313-314)
-    if (cfg.use_residual) {
+    if (cfg.use_residual && !net->hq) {
       const std::string b1 = enc + ".blocks." + std::to_string(d + 1), b2 = enc + ".blocks." + std::to_string(d + 2);
       u1 = up_block(b1 + ".1", b1 + ".2", b1 + ".3", cur, B, h, w, 256, 256, nullptr);
       tap("up1", u1, (size_t)B * 2 * h * 2 * w * 256);
@@ -562,6 +563,10 @@ struct Ctx {
 
 static int check_geometry(femasr_net* net, int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return fail(FEMASR_ERR_ARG, "forward: empty input");
+  if (net->hq) {
+    if (H % 8 || W % 8) return fail(FEMASR_ERR_ARG, "forward (HQ stage): H and W must be multiples of 8");
+    return FEMASR_OK;
+  }
   const int div = net->cfg.scale_factor == 4 ? 2 : 4;
   if (H % 2 || W % 2) return fail(FEMASR_ERR_ARG, "forward: H and W must be even");
   const int hs = H / div, ws = W / div;
@@ -586,14 +591,16 @@ extern "C" int femasr_device_cc(void) {
 
 extern "C" int femasr_net_create(const femasr_net_config* cfg, femasr_net** out) {
   FEMASR_CHECK_ARG(cfg && out, "net_create: null pointer");
-  FEMASR_CHECK_ARG(cfg->scale_factor == 2 || cfg->scale_factor == 4, "net_create: scale_factor must be 2 or 4");
+  FEMASR_CHECK_ARG(cfg->scale_factor == 1 || cfg->scale_factor == 2 || cfg->scale_factor == 4,
+                   "net_create: scale_factor must be 4, 2 (LQ stage) or 1 (HQ autoencoder stage)");
   FEMASR_CHECK_ARG(cfg->in_channel == 3, "net_create: in_channel must be 3");
   FEMASR_CHECK_ARG(cfg->e_dim > 0 && cfg->e_dim % 64 == 0 && cfg->e_dim <= 1024, "net_create: e_dim must be a multiple of 64");
   FEMASR_CHECK_ARG(cfg->n_e > 0 && cfg->n_e % 64 == 0, "net_create: n_e must be a multiple of 64");
   FEMASR_CHECK_ARG(cfg->gemm_path == 0 || cfg->gemm_path == 1, "net_create: gemm_path must be 0 or 1");
   femasr_net* n = new femasr_net();
   n->cfg = *cfg;
-  n->depth = cfg->scale_factor == 4 ? 1 : 2;
+  n->depth = cfg->scale_factor == 4 ? 1 : (cfg->scale_factor == 2 ? 2 : 3);
+  n->hq = cfg->scale_factor == 1;
   if (const char* ev = getenv("FEMASR_TC_PRECISE")) n->tc_precise = atoi(ev) != 0;
   build_spec(n);
   *out = n;
@@ -775,15 +782,16 @@ extern "C" double femasr_net_flops(femasr_net* net, int B, int H, int W) {
   double ch = cin, hh = H, ww = W;
   for (int i = 0; i < d; ++i) {
     hh = std::floor(hh / 2); ww = std::floor(ww / 2);
-    f += 2.0 * 9 * ch * 256 * hh * ww + 4 * 2.0 * 9 * 256 * 256 * hh * ww;
-    ch = 256;
+    const double co = chan((256 / scale) >> (i + 1));
+    f += 2.0 * 9 * ch * co * hh * ww + 4 * 2.0 * 9 * co * co * hh * ww;
+    ch = co;
   }
   const double px = hh * ww;
   const double lin = 2.0 * 256 * (768 + 256 + 1024 + 1024) * px, att = 2 * 2.0 * 64 * 256 * px;
-  f += 4 * (6 * (lin + att) + 2.0 * 9 * 256 * 256 * px);
+  if (!net->hq) f += 4 * (6 * (lin + att) + 2.0 * 9 * 256 * 256 * px);
   f += 2.0 * 256 * e * px + 2.0 * net->cfg.n_e * e * px + 2.0 * 9 * e * 256 * px;
   const double up[2][3] = {{256, 256, 2}, {256, 128, 4}};
-  for (auto& u : up) f += (2.0 * 9 * u[0] * u[1] + 4 * 2.0 * 9 * u[1] * u[1]) * px * u[2] * u[2];
+  if (!net->hq) for (auto& u : up) f += (2.0 * 9 * u[0] * u[1] + 4 * 2.0 * 9 * u[1] * u[1]) * px * u[2] * u[2];
   const double dec[3][3] = {{256, 256, 2}, {256, 128, 4}, {128, 64, 8}};
   for (auto& u : dec) f += (2.0 * 9 * u[0] * u[1] + 4 * 2.0 * 9 * u[1] * u[1]) * px * u[2] * u[2];
   f += 2.0 * 9 * 64 * 3 * px * 64;

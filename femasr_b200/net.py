@@ -134,7 +134,7 @@ class NativeNet:
         s = self.scale
         with torch.cuda.device(self.device):
             y = torch.empty((B, 3, H * s, W * s), dtype=torch.float32, device=self.device)
-            div = 2 if s == 4 else 4
+            div = {4: 2, 2: 4, 1: 8}[s]
             h, w = H // div, W // div
             idx = torch.empty((B, 1, h, w), dtype=torch.int64, device=self.device) if want_indices else None
             loss = torch.empty((), dtype=torch.float32, device=self.device) if want_loss else None
@@ -188,9 +188,9 @@ class NativeNet:
 
     def tap_shapes(self, B: int, H: int, W: int) -> Dict[str, Tuple[int, ...]]:
         s = self.scale
-        div = 2 if s == 4 else 4
+        div = {4: 2, 2: 4, 1: 8}[s]
         h, w = H // div, W // div
-        c0 = 256 if s == 4 else 128
+        c0 = {4: 256, 2: 128, 1: 64}[s]
         return {"in_conv": (B, H - 1, W - 1, c0), "down": (B, h, w, 256), "swin": (B, h, w, 256),
                 "up1": (B, 2 * h, 2 * w, 256), "up2": (B, 4 * h, 4 * w, 128), "z": (B, h, w, self.e_dim),
                 "zq": (B, h, w, self.e_dim), "after_quant": (B, h, w, 256), "dec0": (B, 2 * h, 2 * w, 256),

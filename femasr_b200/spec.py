@@ -48,7 +48,8 @@ def _linear(p: str, ci: int, co: int) -> List[Tuple[str, tuple, str, int]]:
 
 
 def param_spec(scale: int, e_dim: int, n_e: int = 1024, in_channel: int = 3):
-    """Ordered [(name, shape, kind, fan_in)] for LQ_stage=True, one codebook at scale 32.
+    """Ordered [(name, shape, kind, fan_in)] for one codebook at scale 32.  scale 4 | 2: LQ_stage=True;
+    scale 1: the HQ autoencoder (LQ_stage=False, femasr_arch.py:241: scale_factor forced to 1; no Swin, no up branches).
 
     kind: w | b (kaiming-uniform bound 1/sqrt(fan_in)), norm_w | norm_b, rpb (trunc-normal .02),
     rpi | mask (buffers), codebook (U(+-1/n_e)).
@@ -64,7 +65,8 @@ def param_spec(scale: int, e_dim: int, n_e: int = 1024, in_channel: int = 3):
         spec += _res_block(f"{enc}.blocks.{i}.1", co) + _res_block(f"{enc}.blocks.{i}.2", co)
         res //= 2
     C = SWIN_DIM
-    for r in range(N_RSTB):
+    hq = scale == 1
+    for r in range(0 if hq else N_RSTB):
         for b in range(SWIN_DEPTH):
             p = f"{enc}.blocks.{d}.swin_blks.{r}.residual_group.blocks.{b}"
             if b % 2 == 1:
@@ -77,7 +79,7 @@ def param_spec(scale: int, e_dim: int, n_e: int = 1024, in_channel: int = 3):
             spec += [(f"{p}.norm2.weight", (C,), "norm_w", 0), (f"{p}.norm2.bias", (C,), "norm_b", 0)]
             spec += _linear(f"{p}.mlp.fc1", C, MLP_RATIO * C) + _linear(f"{p}.mlp.fc2", MLP_RATIO * C, C)
         spec += _conv(f"{enc}.blocks.{d}.swin_blks.{r}.conv", C, C, 3)
-    for j in (d + 1, d + 2):
+    for j in (() if hq else (d + 1, d + 2)):
         ci, co = CHANNELS[res], CHANNELS[res * 2]
         spec += _conv(f"{enc}.blocks.{j}.1", ci, co, 3)
         spec += _res_block(f"{enc}.blocks.{j}.2", co) + _res_block(f"{enc}.blocks.{j}.3", co)

@@ -175,7 +175,8 @@ def encode_depth(scale: int, gt_res: int = 256, cb_scale: int = 32) -> int:
 
 
 def multiscale_encoder(sd: SD, x: Tensor, scale: int) -> List[Tensor]:
-    """femasr_arch.py:184-192 (LQ stage).  Returns the per-block outputs."""
+    """femasr_arch.py:184-192.  Returns the per-block outputs.  scale 4|2: LQ stage (down, Swin, two up blocks);
+    scale 1: HQ stage (LQ_stage=False: three down blocks only, :166-182)."""
     p = "multiscale_encoder"
     d = encode_depth(scale)
     outs = []
@@ -185,6 +186,8 @@ def multiscale_encoder(sd: SD, x: Tensor, scale: int) -> List[Tensor]:
         x = res_block(sd, f"{p}.blocks.{i}.1", x)
         x = res_block(sd, f"{p}.blocks.{i}.2", x)
         outs.append(x)
+    if scale == 1:
+        return outs
     x = swin_layers(sd, f"{p}.blocks.{d}", x)              # :166-167
     outs.append(x)
     for j in (d + 1, d + 2):                               # :168-180
@@ -228,15 +231,17 @@ def encode_and_decode(sd: SD, x: Tensor, scale: int, taps: dict | None = None):
     Returns (out_img, codebook_loss, semantic_loss, [indices]).  ``taps`` (optional dict)
     receives the stage-boundary tensors used by the stage-level parity tests.
     """
-    feats = multiscale_encoder(sd, x, scale)[-3:]          # :313-314
+    lq = scale != 1
+    outs = multiscale_encoder(sd, x, scale)
+    feats = outs[-3:] if lq else outs[::-1]                # :313-316
     z = _conv(sd, "before_quant_group.0", feats[0], 1, 0)  # 1x1, :337
     zq, loss, idx = vector_quantize(sd["quantize_group.0.embedding.weight"], z)   # :342
     t = _conv(sd, "after_quant_group.0.conv", zq)          # CombineQuantBlock, fema_utils.py:92-99
     if taps is not None:
         taps.update(enc0=feats[0], enc1=feats[1], enc2=feats[2], z=z, zq=zq, after_quant=t)
     for i in range(3):                                     # max_depth = 3, :255
-        if i > 0:
-            t = t + feats[i]                               # :361-362
+        if i > 0 and lq:
+            t = t + feats[i]                               # :361-362 (LQ stage with use_residual only)
         t = decoder_block(sd, f"decoder_group.{i}", t)
         if taps is not None:
             taps[f"dec{i}"] = t
@@ -298,6 +303,7 @@ def test_tile(sd: SD, x: Tensor, scale: int, tile_size: int = 240, tile_pad: int
 
 # --------------------------------------------------------------------------- random-init weights
 def flops_per_image(scale: int, h: int, w: int, e_dim: int) -> float:
+    assert scale in (2, 4), "LQ-stage model"
     """Algorithmic FLOPs (2*MAC over conv + linear + QK^T/PV + VQ distance) of encode_and_decode on
     one h x w LR image.  Matches SURVEY.md section 8a [probe]: x4 128x128 e256 = 754.53 GF."""
     d = encode_depth(scale)

@@ -34,6 +34,9 @@ CASES = [
     ("x2_e512_test", 2, 512, "default", 15, "test", (1, 3, 40, 72), {}),
     ("x4_e256_tile", 4, 256, "perturbed", 16, "test_tile", (1, 3, 72, 56), {"tile_size": 32, "tile_pad": 8}),
     ("x4_e256_decode_indices", 4, 256, "perturbed", 17, "decode_indices", (2, 1, 4, 6), {}),
+    # scale 1 = the HQ autoencoder (LQ_stage=False)
+    ("hq_e512_fwd", 1, 512, "perturbed", 18, "forward", (1, 3, 64, 96), {}),
+    ("hq_e256_test", 1, 256, "default", 19, "test", (1, 3, 40, 72), {}),
 ]
 
 
@@ -55,7 +58,7 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     for name, scale, e_dim, init, seed, entry, shape, extra in CASES:
         sd = random_state_dict(scale, e_dim, seed=seed, init=init)
-        net = ref.FeMaSRNet(codebook_params=[[32, 1024, e_dim]], LQ_stage=True, scale_factor=scale).eval()
+        net = ref.FeMaSRNet(codebook_params=[[32, 1024, e_dim]], LQ_stage=scale != 1, scale_factor=scale).eval()
         net.load_state_dict(sd, strict=True)
         g = torch.Generator().manual_seed(1000 + seed)
         rec = dict(scale=scale, e_dim=e_dim, init=init, seed=seed, entry=entry, digest=sd_digest(sd))
@@ -71,9 +74,10 @@ def main():
         enc = net.multiscale_encoder
         hooks.append(enc.in_conv.register_forward_hook(hook("in_conv")))
         hooks.append(enc.blocks[d - 1].register_forward_hook(hook("down")))
-        hooks.append(enc.blocks[d].register_forward_hook(hook("swin")))
-        hooks.append(enc.blocks[d + 1].register_forward_hook(hook("up1")))
-        hooks.append(enc.blocks[d + 2].register_forward_hook(hook("up2")))
+        if scale != 1:
+            hooks.append(enc.blocks[d].register_forward_hook(hook("swin")))
+            hooks.append(enc.blocks[d + 1].register_forward_hook(hook("up1")))
+            hooks.append(enc.blocks[d + 2].register_forward_hook(hook("up2")))
         hooks.append(net.before_quant_group[0].register_forward_hook(hook("z")))
         hooks.append(net.after_quant_group[0].register_forward_hook(hook("after_quant")))
         for i in range(3):

@@ -36,6 +36,12 @@ def test_argument_validation_without_gpu(built_lib):
     h = ctypes.c_void_p()
     cfg = lib.NetConfig(3, 1024, 256, 3, 1, 1, 0)
     assert L.femasr_net_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    cfg = lib.NetConfig(1, 1024, 256, 3, 1, 1, 1)                 # HQ autoencoder stage
+    assert L.femasr_net_create(ctypes.byref(cfg), ctypes.byref(h)) == 0
+    need = ctypes.c_size_t()
+    assert L.femasr_net_workspace_bytes(h, 2, 64, 96, ctypes.byref(need)) == 0 and need.value > 0
+    assert L.femasr_net_workspace_bytes(h, 2, 60, 96, ctypes.byref(need)) == -1
+    L.femasr_net_destroy(h)
     cfg = lib.NetConfig(4, 1024, 256, 3, 1, 1, 0)
     assert L.femasr_net_create(ctypes.byref(cfg), ctypes.byref(h)) == 0
     need = ctypes.c_size_t()
@@ -62,9 +68,11 @@ def test_no_cpu_fallback(built_lib):
 def test_unsupported_configs_raise():
     from basicsr.archs.femasr_arch import FeMaSRNet
     with pytest.raises(NotImplementedError):
-        FeMaSRNet(codebook_params=[[32, 1024, 256]], LQ_stage=False)
+        FeMaSRNet(codebook_params=[[32, 1024, 256]], LQ_stage=True, norm_type="bn")
     with pytest.raises(NotImplementedError):
         FeMaSRNet(codebook_params=[[32, 1024, 256], [64, 512, 256]], LQ_stage=True)
+    hq = FeMaSRNet(codebook_params=[[32, 1024, 256]], LQ_stage=False, scale_factor=4)    # HQ stage: scale forced to 1
+    assert hq.scale_factor == 1 and not any("swin" in k for k in hq.state_dict())
 
 
 def test_module_copy_and_checkpoint_roundtrip(tmp_path):

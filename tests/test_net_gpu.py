@@ -21,10 +21,10 @@ OUT_ATOL = 1e-3
 
 
 def make_net(scale, e_dim, sd, cuda, **kw):
-    # gemm_path 0: the fp32-FFMA path (ATen-level rounding, tight tolerances below); the default tensor-core
+    # scale 1 = the HQ autoencoder (LQ_stage=False).  gemm_path 0: the fp32-FFMA path (ATen-level rounding, tight tolerances below); the default tensor-core
     # path is exercised against the same goldens in tests/test_tc_gpu.py.
     kw.setdefault("gemm_path", 0)
-    net = FeMaSRNet(codebook_params=[[32, 1024, e_dim]], LQ_stage=True, scale_factor=scale, **kw)
+    net = FeMaSRNet(codebook_params=[[32, 1024, e_dim]], LQ_stage=scale != 1, scale_factor=scale, **kw)
     net.load_state_dict(sd, strict=True)
     return net.to(cuda).eval()
 

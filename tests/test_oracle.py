@@ -33,7 +33,7 @@ def sample(t):
 
 
 def test_golden_present():
-    assert len(GOLDEN) >= 7
+    assert len(GOLDEN) >= 9
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -49,8 +49,11 @@ def test_oracle_matches_reference_golden(path):
             assert np.array_equal(idx[0].numpy(), g["indices"]), "codebook indices must be bit-exact"
             np.testing.assert_allclose(loss.numpy(), g["loss"], rtol=1e-6)
             assert float(sem) == 0.0
-            for ours, theirs in (("enc0", "swin"), ("enc1", "up1"), ("enc2", "up2"), ("z", "z"),
-                                 ("after_quant", "after_quant"), ("dec0", "dec0"), ("dec1", "dec1"), ("dec2", "dec2")):
+            pairs = (("enc0", "swin"), ("enc1", "up1"), ("enc2", "up2"), ("z", "z"),
+                     ("after_quant", "after_quant"), ("dec0", "dec0"), ("dec1", "dec1"), ("dec2", "dec2"))
+            if scale == 1:      # HQ stage: enc_feats are the down blocks reversed; only the last one is hooked
+                pairs = (("enc0", "down"),) + pairs[3:]
+            for ours, theirs in pairs:
                 np.testing.assert_allclose(sample(taps[ours]), g["tap_" + theirs], rtol=0, atol=1e-5)
         elif entry == "test":
             out = O.test(sd, x, scale)

@@ -241,7 +241,7 @@ def test_tc_prologues(cuda):
 
 def make_net(scale, e_dim, sd, cuda):
     from basicsr.archs.femasr_arch import FeMaSRNet
-    net = FeMaSRNet(codebook_params=[[32, 1024, e_dim]], LQ_stage=True, scale_factor=scale, gemm_path=1)
+    net = FeMaSRNet(codebook_params=[[32, 1024, e_dim]], LQ_stage=scale != 1, scale_factor=scale, gemm_path=1)
     net.load_state_dict(sd, strict=True)
     return net.to(cuda).eval()
 
