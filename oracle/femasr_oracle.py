@@ -3,7 +3,8 @@
 This file is a functional restatement, in plain torch-CPU ops driven by a
 ``state_dict``, of what chaofengc/FeMaSR computes on the path
 ``FeMaSRNet.test_tile -> test -> encode_and_decode`` for the in-scope
-configuration (LQ_stage=True, norm 'gn', act 'silu', one codebook, scale 2|4).
+configurations (norm 'gn', act 'silu', one codebook; LQ_stage=True with scale 2|4,
+and the HQ autoencoder LQ_stage=False passed as scale 1).
 It is NOT the product: only ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it, and
 only as the checker / the CPU arm.  The product path (``femasr_b200``) never
