@@ -38,3 +38,41 @@ def test_benchmark_geometry_parity(cuda, gemm_path, max_flips):
         assert diff.max().item() <= 1e-3
     else:
         assert frac_bad <= 0.01      # a flipped code only disturbs its own neighbourhood
+
+
+def test_full_batch_size_independent_properties(cuda):
+    """BASELINE config 2 at its full size (batch 32, 128x128, 131072 VQ rows), where the CPU oracle is too slow to
+    run: properties that must hold regardless of size.  (a) determinism: two runs are bit-identical (fixed-order
+    reductions everywhere); (b) images are independent (GroupNorm per sample, LN per token, attention per window,
+    VQ per pixel): permuting the batch permutes the outputs bit-exactly, and a sub-batch reproduces its rows;
+    (c) indices are valid codes and the reported codebook loss equals 1.25 * mean((e_idx - z)^2) recomputed from the
+    returned stage tensors; (d) the first 4 images agree with the oracle run of test_benchmark_geometry_parity."""
+    B = 32
+    sd = random_state_dict(4, 256, seed=0, init="default")
+    x = torch.rand(B, 3, 128, 128, generator=torch.Generator().manual_seed(1)).to(cuda)
+    net = FeMaSRNet(codebook_params=[[32, 1024, 256]], LQ_stage=True, scale_factor=4)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda).eval()
+    eng = net._native(cuda)
+    y0, l0, i0 = eng.forward(x)
+    y1, l1, i1 = eng.forward(x)
+    assert torch.equal(y0, y1) and torch.equal(i0, i1) and torch.equal(l0, l1), "forward must be deterministic"
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(2)).to(cuda)
+    yp, _, ip = eng.forward(x[perm].contiguous())
+    assert torch.equal(yp, y0[perm]) and torch.equal(ip, i0[perm]), "batch permutation must commute bit-exactly"
+    ys, _, isub = eng.forward(x[5:9].contiguous())
+    assert torch.equal(ys, y0[5:9]) and torch.equal(isub, i0[5:9]), "a sub-batch must reproduce its rows bit-exactly"
+    assert int(i0.min()) >= 0 and int(i0.max()) < 1024 and i0.dtype == torch.int64 and tuple(i0.shape) == (B, 1, 64, 64)
+    _, l2, i2, taps = eng.forward(x, taps=["z", "zq"])
+    z = taps["z"].reshape(-1, 256)
+    e = sd["quantize_group.0.embedding.weight"].to(cuda)[i2.reshape(-1)]
+    want_loss = 1.25 * torch.mean((e - z).double() ** 2)
+    assert abs(l2.item() - want_loss.item()) <= 1e-6 * want_loss.item()
+    assert torch.equal(taps["zq"].reshape(-1, 256), z + (e - z)), "straight-through output must be z + (e_idx - z)"
+    # distances: the chosen code is a true nearest neighbour in exact arithmetic up to the fp32 grid
+    d_sel = ((e - z).double() ** 2).sum(1)
+    zd = z[:4096].double()
+    d_all = (zd * zd).sum(1, keepdim=True) + (sd["quantize_group.0.embedding.weight"].double().to(cuda) ** 2).sum(1) \
+        - 2 * zd @ sd["quantize_group.0.embedding.weight"].double().to(cuda).t()
+    gap = d_sel[:4096] - d_all.min(1).values
+    assert float(gap.max()) <= 2.5e-4, "selected code must be nearest up to fp32 rounding of a ~300-magnitude distance"
