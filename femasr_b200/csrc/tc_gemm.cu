@@ -173,28 +173,38 @@ constexpr int A_PLANE_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 constexpr int STRIP_PX = 130;                         // 128 outputs + one halo pixel each side
 constexpr int STRIP_PLANE_BYTES = 17 * 1024;          // 130 rows x 128 B = 16,640 B, padded to the 1024-B swizzle period
 
-template <int BN, bool PAIR, bool STRIP>
+// BRES = true (strip mode, 64 -> 64 channels): the complete weight matrix (9 taps x 64 x 64, hi + lo = 144 KB) is
+// loaded into shared memory ONCE per CTA and stays resident for all of its tiles; only activation strips stream.
+// These layers are L2->SM bound and 60 % of their remaining L2 traffic was the weight tile re-fetched per tile.
+template <int BN, bool PAIR, bool STRIP, bool BRES = false>
 struct TcCfg {
   static_assert(!(PAIR && STRIP), "strip tiles are single-CTA");
+  static_assert(!BRES || (STRIP && BN == 64), "resident weights: strip mode, 64-wide tiles");
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;                 // weight-tile rows this CTA stages
   static constexpr int B_PLANE_BYTES = B_ROWS * TC_BK * 2;
   // joint A+B stages (normal / pair)
   static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
   static constexpr int STAGES = PAIR ? (BN == 256 ? 3 : 4) : (BN == 256 ? 2 : (BN == 128 ? 3 : 4));
   // separate rings (strip)
-  static constexpr int SA_STAGES = 2, SA_BYTES = 2 * STRIP_PLANE_BYTES;
+  // strip planes: 130 rows x 128 B; padded to 17 KB normally, packed back to back when smem is needed for weights
+  // (fine: TMA and the tensor core both derive the swizzle from the absolute address, 128-B alignment suffices)
+  static constexpr int SA_PLANE = BRES ? STRIP_PX * TC_BK * 2 : STRIP_PLANE_BYTES;
+  static constexpr int SA_STAGES = 2, SA_BYTES = 2 * SA_PLANE;
+  static constexpr int B_RES_BYTES = BRES ? 9 * 2 * B_PLANE_BYTES : 0;
   static constexpr int SB_BYTES = 2 * B_PLANE_BYTES;
   static constexpr int NSPLIT = nsplit_for(BN), EPI_WARPS = 4 * NSPLIT, THREADS = tc_threads_for(BN);
   static constexpr int SB_BUDGET = 232448 - 1024 - 256 - EPI_WARPS * 2048 - SA_STAGES * SA_BYTES;   // what is left of 227 KB
-  static constexpr int SB_STAGES = SB_BUDGET / SB_BYTES > 6 ? 6 : SB_BUDGET / SB_BYTES;
-  static constexpr int PIPE_BYTES = STRIP ? SA_STAGES * SA_BYTES + SB_STAGES * SB_BYTES : STAGES * STAGE_BYTES;
-  static constexpr int NBAR_PIPE = STRIP ? 2 * SA_STAGES + 2 * SB_STAGES : 2 * STAGES;   // full/empty barriers of the rings
+  static constexpr int SB_STAGES = BRES ? 0 : (SB_BUDGET / SB_BYTES > 6 ? 6 : SB_BUDGET / SB_BYTES);
+  static constexpr int PIPE_BYTES = BRES ? B_RES_BYTES + SA_STAGES * SA_BYTES
+                                         : (STRIP ? SA_STAGES * SA_BYTES + SB_STAGES * SB_BYTES : STAGES * STAGE_BYTES);
+  // full/empty barriers of the rings (resident weights: one "weights landed" barrier instead of a weight ring)
+  static constexpr int NBAR_PIPE = BRES ? 2 * SA_STAGES + 1 : (STRIP ? 2 * SA_STAGES + 2 * SB_STAGES : 2 * STAGES);
   static constexpr int EPI_BYTES = EPI_WARPS * 2048 /*per-warp 32x16 fp32 transpose tiles*/;
   static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators; power of two for BN in {64,128,256}
   static_assert(8 * (NBAR_PIPE + 4) + 4 <= 256, "barrier area");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-  static_assert(!STRIP || SB_STAGES >= 2, "strip weight ring too small");
+  static_assert(!STRIP || BRES || SB_STAGES >= 2, "strip weight ring too small");
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -240,11 +250,11 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
-template <int BN, bool PAIR, bool STRIP>
+template <int BN, bool PAIR, bool STRIP, bool BRES>
 __global__ void __launch_bounds__(tc_threads_for(BN), 1)
 tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcP p) {
-  using Cfg = TcCfg<BN, PAIR, STRIP>;
+  using Cfg = TcCfg<BN, PAIR, STRIP, BRES>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -321,6 +331,15 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     // ===================== TMA producer (strip mode) =====================
     // per (kh, 64-channel chunk): one 130-pixel activation strip (hi, lo), then the three taps' weight tiles
     int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+    if (BRES) {
+      // the whole [64][9*64] weight matrix (hi, lo) once: tap t at smem_base + t * 2 * B_PLANE_BYTES
+      const uint32_t bres_bar = bar_base + 8u * (2 * Cfg::SA_STAGES);
+      mbar_expect_tx(bres_bar, Cfg::B_RES_BYTES);
+      for (int tap = 0; tap < 9; ++tap) {
+        tma_load_2d(smem_base + tap * 2 * Cfg::B_PLANE_BYTES, &map_b_hi, bres_bar, tap * p.Cin, 0);
+        tma_load_2d(smem_base + tap * 2 * Cfg::B_PLANE_BYTES + Cfg::B_PLANE_BYTES, &map_b_lo, bres_bar, tap * p.Cin, 0);
+      }
+    }
     for (int work = worker; work < num_work; work += nworkers) {
       const TileCoord tc = decode(work);
       const int x0 = tc.tx * p.Wt, y0 = tc.ty, n0 = tc.nt * BN;
@@ -328,15 +347,17 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         for (int cc = 0; cc < p.cchunks; ++cc) {
           const int c0 = cc * TC_BK;
           mbar_wait(emptyA_bar(sa), pa ^ 1u);
-          const uint32_t a_dst = smem_base + sa * Cfg::SA_BYTES;
+          const uint32_t a_dst = smem_base + Cfg::B_RES_BYTES + sa * Cfg::SA_BYTES;
           mbar_expect_tx(fullA_bar(sa), 2 * STRIP_PX * TC_BK * 2);
           tma_load_4d(a_dst, &map_a_hi, fullA_bar(sa), c0, x0 - 1, y0 + kh - 1, tc.b);
-          tma_load_4d(a_dst + STRIP_PLANE_BYTES, &map_a_lo, fullA_bar(sa), c0, x0 - 1, y0 + kh - 1, tc.b);
+          tma_load_4d(a_dst + Cfg::SA_PLANE, &map_a_lo, fullA_bar(sa), c0, x0 - 1, y0 + kh - 1, tc.b);
           if (++sa == Cfg::SA_STAGES) { sa = 0; pa ^= 1u; }
+          if (BRES) continue;
           for (int kw = 0; kw < 3; ++kw) {
             const int tap = kh * 3 + kw;
             mbar_wait(emptyB_bar(sb), pb ^ 1u);
             const uint32_t b_dst = smem_base + Cfg::SA_STAGES * Cfg::SA_BYTES + sb * Cfg::SB_BYTES;
+            (void)n0;
             mbar_expect_tx(fullB_bar(sb), Cfg::SB_BYTES);
             tma_load_2d(b_dst, &map_b_hi, fullB_bar(sb), tap * p.Cin + c0, n0);
             tma_load_2d(b_dst + Cfg::B_PLANE_BYTES, &map_b_lo, fullB_bar(sb), tap * p.Cin + c0, n0);
@@ -349,6 +370,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
     int acc = 0; uint32_t acc_phase = 0;
+    if (BRES) { mbar_wait(bar_base + 8u * (2 * Cfg::SA_STAGES), 0u); tc_fence_after(); }   // weights resident
     for (int work = worker; work < num_work; work += nworkers) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
@@ -358,17 +380,22 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         for (int cc = 0; cc < p.cchunks; ++cc) {
           mbar_wait(fullA_bar(sa), pa);
           tc_fence_after();
-          const uint32_t a_base = smem_base + sa * Cfg::SA_BYTES;
+          const uint32_t a_base = smem_base + Cfg::B_RES_BYTES + sa * Cfg::SA_BYTES;
           for (int kw = 0; kw < 3; ++kw) {
-            mbar_wait(fullB_bar(sb), pb);
-            tc_fence_after();
-            const uint32_t b_base = smem_base + Cfg::SA_STAGES * Cfg::SA_BYTES + sb * Cfg::SB_BYTES;
+            uint32_t b_base;
+            if (BRES) {
+              b_base = smem_base + (kh * 3 + kw) * 2 * Cfg::B_PLANE_BYTES;
+            } else {
+              mbar_wait(fullB_bar(sb), pb);
+              tc_fence_after();
+              b_base = smem_base + Cfg::SA_STAGES * Cfg::SA_BYTES + sb * Cfg::SB_BYTES;
+            }
             // tap kw = the strip shifted by kw pixel rows.  Measured on B200: the tensor core derives the 128B-swizzle
             // XOR from the absolute shared-memory address bits (like TMA does when it writes the strip), so a start
             // address that is 128-byte but not 1024-byte aligned just works with base-offset 0; putting the row phase
             // into the descriptor's base-offset field (bits 49-51) instead produces garbage.
             const uint64_t a_hi = make_sw128_desc(a_base + kw * 128);
-            const uint64_t a_lo = make_sw128_desc(a_base + STRIP_PLANE_BYTES + kw * 128);
+            const uint64_t a_lo = make_sw128_desc(a_base + Cfg::SA_PLANE + kw * 128);
             const uint64_t b_hi = make_sw128_desc(b_base), b_lo = make_sw128_desc(b_base + Cfg::B_PLANE_BYTES);
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
@@ -378,8 +405,10 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
               umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
               umma_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
             }
-            umma_commit(emptyB_bar(sb));
-            if (++sb == Cfg::SB_STAGES) { sb = 0; pb ^= 1u; }
+            if (!BRES) {
+              umma_commit(emptyB_bar(sb));
+              if (++sb == Cfg::SB_STAGES) { sb = 0; pb ^= 1u; }
+            }
           }
           umma_commit(emptyA_bar(sa));
           if (++sa == Cfg::SA_STAGES) { sa = 0; pa ^= 1u; }
@@ -819,18 +848,18 @@ static int sm_count() {
   return g_sm_count;
 }
 
-template <int BN, bool PAIR, bool STRIP>
+template <int BN, bool PAIR, bool STRIP, bool BRES = false>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                      const TcP& p, cudaStream_t st) {
-  using Cfg = TcCfg<BN, PAIR, STRIP>;
+  using Cfg = TcCfg<BN, PAIR, STRIP, BRES>;
   static bool attr_set = false;
   if (!attr_set) {
-    FEMASR_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<BN, PAIR, STRIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    FEMASR_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<BN, PAIR, STRIP, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   if constexpr (!PAIR) {
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    tc_igemm_kernel<BN, false, STRIP><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
+    tc_igemm_kernel<BN, false, STRIP, BRES><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
     return launch_status("tc_igemm_kernel");
   } else {
     const int num_m = p.num_tiles / p.n_tiles;
@@ -843,7 +872,7 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    FEMASR_CUDA(cudaLaunchKernelEx(&cfg, tc_igemm_kernel<BN, true, false>, ah, al, bh, bl, p));
+    FEMASR_CUDA(cudaLaunchKernelEx(&cfg, tc_igemm_kernel<BN, true, false, false>, ah, al, bh, bl, p));
     return launch_status("tc_igemm_kernel(pair)");
   }
 }
@@ -1036,6 +1065,9 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   cudaStream_t st = as_stream(stream);
   if (strip) {
     if (BN == 128) return launch_tc<128, false, true>(mah, mal, mbh, mbl, p, st);
+    // 64 -> 64 channels: weights resident in shared memory (FEMASR_TC_BRES=0 falls back to the streamed weight ring)
+    static const int bres_env = [] { const char* e = getenv("FEMASR_TC_BRES"); return e ? atoi(e) : 1; }();
+    if (bres_env && a->Cin == 64 && a->Cout == 64) return launch_tc<64, false, true, true>(mah, mal, mbh, mbl, p, st);
     return launch_tc<64, false, true>(mah, mal, mbh, mbl, p, st);
   }
   if (pair) {

@@ -27,9 +27,12 @@ def timeit(fn, reps=5):
 
 PAIR = int(os.environ.get('MB_PAIR', '-1'))
 STRIP = int(os.environ.get('MB_STRIP', '-1'))
+ONLY = os.environ.get('MB_ONLY', '')        # substring filter on the case name
 
 
 def conv_case(name, B, H, W, Cin, Cout, ksize=3, up=0, res=False, act=0, split=False, bias=True):
+    if ONLY and ONLY not in name:
+        return 0.0
     hi = (torch.randn(B, H, W, Cin, device=dev) * 0.5).half()
     lo = (torch.randn(B, H, W, Cin, device=dev) * 1e-4).half()
     w = torch.randn(Cout, Cin, ksize, ksize, device=dev) * 0.03

@@ -163,7 +163,9 @@ def test_tc_cta_pair(cuda, B, H, W, Cin, Cout, kw):
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 6, 128, 64, 64), (2, 5, 200, 64, 64), (1, 9, 384, 128, 128),
-                                           (1, 4, 130, 256, 128), (2, 7, 256, 128, 64)])
+                                           (1, 4, 130, 256, 128), (2, 7, 256, 128, 64),
+                                           # 64 -> 64: weights resident in smem; > 148 tiles so CTAs loop over several
+                                           (4, 48, 256, 64, 64)])
 def test_tc_strip_mode(cuda, B, H, W, Cin, Cout):
     """Row-strip tiles: the three horizontal taps read one shared 130-pixel activation strip through descriptors
     offset by kw rows."""
