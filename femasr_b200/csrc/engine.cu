@@ -102,6 +102,7 @@ struct femasr_net {
   int last_launches = 0;
   bool profile = false;
   bool tc_precise = true;                 // K-sliced fp32 accumulation for the layers in front of the VQ
+  bool fast_silu = true;                  // approximate-unit SiLU in the operand staging behind the VQ (FEMASR_FAST_SILU=0: exact)
   std::vector<ProfRec> prof;
   std::string prof_json;
   ~femasr_net() {
@@ -277,11 +278,15 @@ struct Ctx {
       alo = ar.alloc((plane_halves + 1) / 2);
     }
     if (!dry() && ok()) {
-      if (!pre_hi)
+      if (!pre_hi) {
+        // behind the VQ (bar: 1e-3 on the output) the SiLU uses the approximate exp/reciprocal units
+        const int pmode = (prologue == FEMASR_PRO_GN_SILU && !precise && !precise_region && net->fast_silu)
+                              ? FEMASR_PRO_GN_SILU_FAST : prologue;
         run("tc_prepare", 0.0, [&] {
-          return femasr_tc_prepare(x, ahi, alo, prologue, pa, pb, gamma, beta, B, Hin, Win, Cin, 0,
+          return femasr_tc_prepare(x, ahi, alo, pmode, pa, pb, gamma, beta, B, Hin, Win, Cin, 0,
                                    prologue == FEMASR_PRO_LN ? 1e-5f : 1e-6f, st);
         });
+      }
       femasr_tc_args t;
       memset(&t, 0, sizeof(t));
       t.a_hi = pre_hi ? pre_hi : ahi; t.a_lo = pre_hi ? pre_lo : alo;
@@ -602,6 +607,7 @@ extern "C" int femasr_net_create(const femasr_net_config* cfg, femasr_net** out)
   n->depth = cfg->scale_factor == 4 ? 1 : (cfg->scale_factor == 2 ? 2 : 3);
   n->hq = cfg->scale_factor == 1;
   if (const char* ev = getenv("FEMASR_TC_PRECISE")) n->tc_precise = atoi(ev) != 0;
+  if (const char* ev = getenv("FEMASR_FAST_SILU")) n->fast_silu = atoi(ev) != 0;
   build_spec(n);
   *out = n;
   return FEMASR_OK;

@@ -723,6 +723,52 @@ __global__ void __launch_bounds__(256) tc_prepare_kernel(const float* __restrict
   }
 }
 
+// Same transform without replication, organised for bandwidth: the image is a flat array of float4 (4 channels), a warp
+// reads 512 contiguous bytes per request and every thread keeps PREP_U independent requests in flight; blockIdx.y = b.
+constexpr int PREP_U = 4;
+template <int MODE>
+__global__ void __launch_bounds__(256) tc_prepare_flat_kernel(const float4* __restrict__ x, uint2* __restrict__ hi,
+                                                              uint2* __restrict__ lo, const float* __restrict__ sc,
+                                                              const float* __restrict__ sh, int C, int per_image4) {
+  const int b = blockIdx.y;
+  const long base = (long)b * per_image4;
+  const int i0 = blockIdx.x * (256 * PREP_U) + threadIdx.x;
+  const int c4 = C >> 2;
+  float4 v[PREP_U];
+#pragma unroll
+  for (int u = 0; u < PREP_U; ++u) {
+    const int i = i0 + u * 256;
+    if (i < per_image4) v[u] = __ldg(x + base + i);
+  }
+#pragma unroll
+  for (int u = 0; u < PREP_U; ++u) {
+    const int i = i0 + u * 256;
+    if (i >= per_image4) break;
+    float w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+    if (MODE == FEMASR_PRO_GN_SILU || MODE == FEMASR_PRO_GN_SILU_FAST) {
+      const int c = (i % c4) * 4;
+      const float4 s = __ldg(reinterpret_cast<const float4*>(sc + (long)b * C + c));
+      const float4 t = __ldg(reinterpret_cast<const float4*>(sh + (long)b * C + c));
+      const float ss[4] = {s.x, s.y, s.z, s.w}, tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float n = fmaf(w[k], ss[k], tt[k]);
+        // fast form: 2 MUFU + 3 FP32 ops instead of ~25 instructions (this pass is issue-bound with the exact one)
+        w[k] = MODE == FEMASR_PRO_GN_SILU_FAST ? __fdividef(n, 1.0f + __expf(-n)) : silu_f(n);
+      }
+    }
+    __align__(8) __half h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float cl = fminf(fmaxf(w[k], -65504.f), 65504.f);
+      h[k] = __float2half_rn(cl);
+      l[k] = __float2half_rn(cl - __half2float(h[k]));
+    }
+    hi[base + i] = *reinterpret_cast<const uint2*>(h);
+    lo[base + i] = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
 // LayerNorm (C = 256, eps) fused with the split: one warp per token row.
 __global__ void __launch_bounds__(256) tc_prepare_ln_kernel(const float* __restrict__ x, __half* __restrict__ hi,
                                                             __half* __restrict__ lo, const float* __restrict__ gamma,
@@ -980,8 +1026,26 @@ extern "C" int femasr_tc_prepare(const float* x, void* a_hi, void* a_lo, int mod
     tc_prepare_ln_kernel<<<(unsigned)cdiv(M, 8), 256, 0, st>>>(x, hi, lo, gamma, beta, M, eps);
     return launch_status("tc_prepare_ln_kernel");
   }
+  static const int flat_env = [] { const char* e = getenv("FEMASR_PREP_FLAT"); return e ? atoi(e) : 1; }();
+  if (!upsample && flat_env && (long)H * W * (C / 4) < (1l << 30) && B <= 65535 &&
+      (mode == FEMASR_PRO_GN_SILU || mode == FEMASR_PRO_GN_SILU_FAST || mode == FEMASR_PRO_NONE)) {
+    const int per4 = H * W * (C / 4);
+    const dim3 grid((unsigned)cdiv(per4, 256 * PREP_U), (unsigned)B);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    if (mode == FEMASR_PRO_GN_SILU) {
+      FEMASR_CHECK_ARG(pro_a && pro_b, "tc_prepare: GN mode needs the scale/shift tables");
+      tc_prepare_flat_kernel<FEMASR_PRO_GN_SILU><<<grid, 256, 0, st>>>(x4, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), pro_a, pro_b, C, per4);
+    } else if (mode == FEMASR_PRO_GN_SILU_FAST) {
+      FEMASR_CHECK_ARG(pro_a && pro_b, "tc_prepare: GN mode needs the scale/shift tables");
+      tc_prepare_flat_kernel<FEMASR_PRO_GN_SILU_FAST><<<grid, 256, 0, st>>>(x4, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), pro_a, pro_b, C, per4);
+    } else {
+      tc_prepare_flat_kernel<FEMASR_PRO_NONE><<<grid, 256, 0, st>>>(x4, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), nullptr, nullptr, C, per4);
+    }
+    return launch_status("tc_prepare_flat_kernel");
+  }
   const long total8 = (long)B * H * W * (C / 8);
   const unsigned grid = (unsigned)cdiv(total8, 256);
+  if (mode == FEMASR_PRO_GN_SILU_FAST) mode = FEMASR_PRO_GN_SILU;     // replicating variant: exact SiLU only
   if (mode == FEMASR_PRO_GN_SILU) {
     FEMASR_CHECK_ARG(pro_a && pro_b, "tc_prepare: GN mode needs the scale/shift tables");
     tc_prepare_kernel<FEMASR_PRO_GN_SILU><<<grid, 256, 0, st>>>(x, hi, lo, pro_a, pro_b, H, W, C, upsample, total8);

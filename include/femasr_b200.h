@@ -118,7 +118,10 @@ int femasr_output_to_u8(const float* y_nchw, uint8_t* bgr_hwc, int B, int SH, in
  * (linear weights [N,K] are the kh=kw=1 case). */
 int femasr_pack_weight(const float* w_oihw, float* w_packed, int Cout, int Cin, int kh, int kw, void* stream);
 
-enum { FEMASR_PRO_NONE = 0, FEMASR_PRO_GN_SILU = 1, FEMASR_PRO_LN = 2 };
+enum { FEMASR_PRO_NONE = 0, FEMASR_PRO_GN_SILU = 1, FEMASR_PRO_LN = 2,
+       /* femasr_tc_prepare only: GN + SiLU with ex2.approx / rcp.approx (relative error <= 4e-7 instead of 1.2e-7);
+          the engine uses it behind the VQ, where the bar is 1e-3 on the output, never in front of the index decision */
+       FEMASR_PRO_GN_SILU_FAST = 3 };
 enum { FEMASR_ACT_NONE = 0, FEMASR_ACT_GELU = 1 };
 
 /* Implicit-GEMM convolution / linear:  y = act(conv(pro(x)) + bias) + res1 + res2.

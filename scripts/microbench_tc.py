@@ -67,3 +67,24 @@ print("# upsample-fused (sub-pixel) convs, low-res input size given")
 conv_case("up 256->256 @64->128", 32, 64, 64, 256, 256, up=1)
 conv_case("up 256->128 @128->256", 32, 128, 128, 256, 128, up=1)
 conv_case("up 128->64 @256->512", 32, 256, 256, 128, 64, up=1)
+
+
+def prep_case(name, B, H, W, C, mode):
+    if ONLY and ONLY not in name:
+        return
+    from femasr_b200 import lib as L
+    x = torch.randn(B, H, W, C, device=dev)
+    sc, sh = torch.rand(B, C, device=dev) + 0.5, torch.randn(B, C, device=dev) * 0.1
+    hi = torch.empty(B, H, W, C, dtype=torch.float16, device=dev); lo = torch.empty_like(hi)
+    lib = L.load()
+    fn = lambda: L.check(lib.femasr_tc_prepare(G.p(x), G.p(hi), G.p(lo), mode, G.p(sc), G.p(sh), None, None, B, H, W, C, 0, 1e-6, G.S()))
+    ms = timeit(fn)
+    print(f"{name:34s} {ms:8.3f} ms  {x.numel() * 8 / ms / 1e6:7.1f} GB/s (4 B read + 4 B written per element)")
+
+
+print("# operand staging (GN + SiLU + fp16 split), batch 32")
+for mode, tag in ((1, "exact"), (3, "fast")):
+    prep_case(f"prep {tag} 64ch @512x512", 32, 512, 512, 64, mode)
+    prep_case(f"prep {tag} 128ch @256x256", 32, 256, 256, 128, mode)
+    prep_case(f"prep {tag} 256ch @128x128", 32, 128, 128, 256, mode)
+prep_case("prep none 256ch @64x64", 32, 64, 64, 256, 0)

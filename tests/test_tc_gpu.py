@@ -233,6 +233,21 @@ def test_tc_prologues(cuda):
     hi, lo = G.tc_prepare(xg, L.PRO_GN_SILU, sc, sh)
     got = (hi.float() + lo.float()).permute(0, 3, 1, 2).cpu()
     assert (got - want).abs().max().item() <= 5e-6
+    # approximate-unit SiLU (used behind the VQ only): a few 1e-7 of max(|v|, 1)
+    hf, lf = G.tc_prepare(xg, L.PRO_GN_SILU_FAST, sc, sh)
+    gotf = (hf.float() + lf.float()).permute(0, 3, 1, 2).cpu()
+    err = ((gotf - want).abs() / want.abs().clamp_min(1.0)).max().item()
+    print(f"fast SiLU staging: max err / max(|v|,1) {err:.2e}, max abs {(gotf - want).abs().max().item():.2e}")
+    assert err <= 2e-6
+    # odd sizes: the flat kernel's tail (per-image float4 count not a multiple of 1024)
+    x3 = rnd(3, 64, 5, 7, seed=15, scale=2.0)
+    g3, b3 = 1 + 0.2 * rnd(64, seed=16), 0.2 * rnd(64, seed=17)
+    want3 = F.silu(F.group_norm(x3, 32, g3, b3, 1e-6))
+    x3g = G.nhwc(x3).to(cuda)
+    sc3, sh3 = G.gn_tables(x3g, g3.to(cuda), b3.to(cuda))
+    for mode in (L.PRO_GN_SILU, L.PRO_GN_SILU_FAST):
+        h3, l3 = G.tc_prepare(x3g, mode, sc3, sh3)
+        assert ((h3.float() + l3.float()).permute(0, 3, 1, 2).cpu() - want3).abs().max().item() <= 5e-6
     t = rnd(777, 256, seed=12, scale=2.0) + 0.3
     g2, b2 = 1 + 0.2 * rnd(256, seed=13), 0.2 * rnd(256, seed=14)
     want = F.layer_norm(t, (256,), g2, b2, 1e-5)
