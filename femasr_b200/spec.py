@@ -47,9 +47,26 @@ def _linear(p: str, ci: int, co: int) -> List[Tuple[str, tuple, str, int]]:
     return [(f"{p}.weight", (co, ci), "w", ci), (f"{p}.bias", (co,), "b", ci)]
 
 
-def param_spec(scale: int, e_dim: int, n_e: int = 1024, in_channel: int = 3):
-    """Ordered [(name, shape, kind, fan_in)] for one codebook at scale 32.  scale 4 | 2: LQ_stage=True;
+def normalize_codebooks(codebooks, n_e: int = 1024, e_dim: int = 256):
+    """[(scale, n_e, e_dim), ...] as ints (the reference's ``codebook_params`` rows, femasr_arch.py:231-235).
+    The first codebook must sit at scale 32 (it fixes the encoder/decoder depth, :255-256); further ones at
+    strictly increasing decoder resolutions 64 / 128 (:329-331)."""
+    if codebooks is None:
+        return [(CB_SCALE, int(n_e), int(e_dim))]
+    cbs = [(int(s), int(n), int(e)) for s, n, e in codebooks]
+    if not cbs or cbs[0][0] != CB_SCALE:
+        raise NotImplementedError("the first codebook must be at scale 32")
+    scales = [s for s, _, _ in cbs]
+    if any(s not in (32, 64, 128) for s in scales) or scales != sorted(set(scales)):
+        raise NotImplementedError(f"codebook scales must be an increasing subset of 32, 64, 128, got {scales}")
+    return cbs
+
+
+def param_spec(scale: int, e_dim: int, n_e: int = 1024, in_channel: int = 3, codebooks=None):
+    """Ordered [(name, shape, kind, fan_in)].  scale 4 | 2: LQ_stage=True;
     scale 1: the HQ autoencoder (LQ_stage=False, femasr_arch.py:241: scale_factor forced to 1; no Swin, no up branches).
+    ``codebooks`` = [(scale, n_e, e_dim), ...] for the multi-scale variant (femasr_arch.py:280-299); default: one
+    codebook (32, n_e, e_dim).
 
     kind: w | b (kaiming-uniform bound 1/sqrt(fan_in)), norm_w | norm_b, rpb (trunc-normal .02),
     rpi | mask (buffers), codebook (U(+-1/n_e)).
@@ -90,9 +107,12 @@ def param_spec(scale: int, e_dim: int, n_e: int = 1024, in_channel: int = 3):
         spec += _conv(f"decoder_group.{i}.block.1", ci, co, 3)
         spec += _res_block(f"decoder_group.{i}.block.2", co) + _res_block(f"decoder_group.{i}.block.3", co)
     spec += _conv("out_conv", CHANNELS[GT_RES], 3, 3)
-    spec.append(("quantize_group.0.embedding.weight", (n_e, e_dim), "codebook", n_e))
-    spec += _conv("before_quant_group.0", CHANNELS[CB_SCALE], e_dim, 1)
-    spec += _conv("after_quant_group.0.conv", e_dim, CHANNELS[CB_SCALE], 3)
+    cbs = normalize_codebooks(codebooks, n_e, e_dim)
+    for k, (cs, ne, ed) in enumerate(cbs):                 # femasr_arch.py:280-299
+        ch = CHANNELS[cs]
+        spec.append((f"quantize_group.{k}.embedding.weight", (ne, ed), "codebook", ne))
+        spec += _conv(f"before_quant_group.{k}", ch if k == 0 else 2 * ch, ed, 1)
+        spec += _conv(f"after_quant_group.{k}.conv", ed if k == 0 else cbs[k - 1][2] + ed, ch, 3)
     return spec
 
 
@@ -128,7 +148,7 @@ def _gen(seed: int, name: str) -> torch.Generator:
 
 
 def random_state_dict(scale: int, e_dim: int, seed: int = 0, init: str = "default",
-                      n_e: int = 1024) -> Dict[str, torch.Tensor]:
+                      n_e: int = 1024, codebooks=None) -> Dict[str, torch.Tensor]:
     """Seeded random weights with the reference's default-init distributions.
 
     Each tensor is drawn from its own generator keyed by (seed, name), so the dict is reproducible
@@ -138,7 +158,7 @@ def random_state_dict(scale: int, e_dim: int, seed: int = 0, init: str = "defaul
     parameters and the codebook get non-trivial values so tests exercise them.
     """
     sd: Dict[str, torch.Tensor] = {}
-    for name, shape, kind, fan_in in param_spec(scale, e_dim, n_e):
+    for name, shape, kind, fan_in in param_spec(scale, e_dim, n_e, codebooks=codebooks):
         g = _gen(seed, name)
         if kind in ("w", "b"):
             bound = 1.0 / math.sqrt(fan_in)
@@ -160,7 +180,7 @@ def random_state_dict(scale: int, e_dim: int, seed: int = 0, init: str = "defaul
             t = shift_attn_mask(SWIN_INIT_RES, SWIN_INIT_RES)
         elif kind == "codebook":
             if init == "default":
-                t = (torch.rand(shape, generator=g) * 2 - 1) / n_e
+                t = (torch.rand(shape, generator=g) * 2 - 1) / fan_in      # fan_in carries this codebook's n_e
             else:
                 t = torch.randn(shape, generator=g) * 0.5
         else:

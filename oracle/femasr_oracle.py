@@ -3,8 +3,9 @@
 This file is a functional restatement, in plain torch-CPU ops driven by a
 ``state_dict``, of what chaofengc/FeMaSR computes on the path
 ``FeMaSRNet.test_tile -> test -> encode_and_decode`` for the in-scope
-configurations (norm 'gn', act 'silu', one codebook; LQ_stage=True with scale 2|4,
-and the HQ autoencoder LQ_stage=False passed as scale 1).
+configurations (norm 'gn', act 'silu'; one codebook at scale 32 or the multi-scale
+variant with further codebooks at 64 / 128; LQ_stage=True with scale 2|4, and the HQ
+autoencoder LQ_stage=False passed as scale 1; optional gt_indices loss branch).
 It is NOT the product: only ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it, and
 only as the checker / the CPU arm.  The product path (``femasr_b200``) never
@@ -204,8 +205,19 @@ def vq_dist(z: Tensor, cb: Tensor) -> Tensor:
     return torch.sum(z ** 2, dim=1, keepdim=True) + torch.sum(cb ** 2, dim=1) - 2 * torch.matmul(z, cb.t())
 
 
-def vector_quantize(cb: Tensor, z_nchw: Tensor):
-    """femasr_arch.py:50-100 (LQ stage, gt_indices=None).  Returns (z_q NCHW, loss, idx [B,1,h,w])."""
+def gram_loss(x: Tensor, y: Tensor) -> Tensor:
+    """femasr_arch.py:40-48: mean squared difference of the per-image [c,c] Gram matrices (x, y: [b,h,w,c])."""
+    b, h, w, c = x.shape
+    x = x.reshape(b, h * w, c)
+    y = y.reshape(b, h * w, c)
+    gmx = x.transpose(1, 2) @ x / (h * w)
+    gmy = y.transpose(1, 2) @ y / (h * w)
+    return (gmx - gmy).square().mean()
+
+
+def vector_quantize(cb: Tensor, z_nchw: Tensor, gt_indices: Tensor | None = None, lq: bool = True):
+    """femasr_arch.py:50-100.  Returns (z_q NCHW, loss, idx [B,1,h,w]).  ``gt_indices`` (the HQ stage's codes,
+    any shape with B*h*w entries) only changes the loss, and only in the LQ stage (:84-92)."""
     z = z_nchw.permute(0, 2, 3, 1).contiguous()
     zf = z.view(-1, cb.shape[1])
     d = vq_dist(zf, cb)
@@ -213,7 +225,12 @@ def vector_quantize(cb: Tensor, z_nchw: Tensor):
     zq = cb[idx].view(z.shape)                             # == onehot @ codebook, :67-82
     e_lat = torch.mean((zq - z) ** 2)
     q_lat = torch.mean((zq - z) ** 2)
-    loss = q_lat + e_lat * VQ_BETA                         # :92
+    if lq and gt_indices is not None:                      # :70-78, :87-90
+        zq_gt = cb[gt_indices.reshape(-1)].view(z.shape)
+        loss = VQ_BETA * ((zq_gt - z) ** 2).mean()
+        loss = loss + gram_loss(z, zq_gt)
+    else:
+        loss = q_lat + e_lat * VQ_BETA                     # :92
     zq = z + (zq - z)                                      # straight-through, :95 (not bit-equal to zq)
     zq = zq.permute(0, 3, 1, 2).contiguous()
     return zq, loss, idx.reshape(zq.shape[0], 1, zq.shape[2], zq.shape[3])
@@ -226,28 +243,50 @@ def decoder_block(sd: SD, p: str, x: Tensor) -> Tensor:
     return res_block(sd, p + ".block.3", x)
 
 
-def encode_and_decode(sd: SD, x: Tensor, scale: int, taps: dict | None = None):
-    """femasr_arch.py:311-374 for LQ_stage=True, single codebook at res 32, use_residual=True.
+def encode_and_decode(sd: SD, x: Tensor, scale: int, taps: dict | None = None, cb_scales=(32,),
+                      gt_indices=None, use_residual: bool = True, use_quantize: bool = True):
+    """femasr_arch.py:311-374.  ``cb_scales``: decoder resolutions that carry a codebook (first one 32, :231);
+    ``gt_indices``: list of index maps, one per codebook (loss only, :339-342).
 
-    Returns (out_img, codebook_loss, semantic_loss, [indices]).  ``taps`` (optional dict)
+    Returns (out_img, codebook_loss, semantic_loss, [indices per codebook]).  ``taps`` (optional dict)
     receives the stage-boundary tensors used by the stage-level parity tests.
     """
     lq = scale != 1
     outs = multiscale_encoder(sd, x, scale)
     feats = outs[-3:] if lq else outs[::-1]                # :313-316
-    z = _conv(sd, "before_quant_group.0", feats[0], 1, 0)  # 1x1, :337
-    zq, loss, idx = vector_quantize(sd["quantize_group.0.embedding.weight"], z)   # :342
-    t = _conv(sd, "after_quant_group.0.conv", zq)          # CombineQuantBlock, fema_utils.py:92-99
     if taps is not None:
-        taps.update(enc0=feats[0], enc1=feats[1], enc2=feats[2], z=z, zq=zq, after_quant=t)
+        taps.update(enc0=feats[0], enc1=feats[1], enc2=feats[2])
+    losses, indices = [], []
+    k = 0
+    prev_dec = prev_quant = None
+    t = feats[0]
     for i in range(3):                                     # max_depth = 3, :255
-        if i > 0 and lq:
-            t = t + feats[i]                               # :361-362 (LQ stage with use_residual only)
+        if 32 * 2 ** i in cb_scales:                       # :330-331
+            bq = feats[i] if prev_dec is None else torch.cat((feats[i], prev_dec), dim=1)     # :332-335
+            z = _conv(sd, f"before_quant_group.{k}", bq, 1, 0)                                 # 1x1, :337
+            zq, loss, idx = vector_quantize(sd[f"quantize_group.{k}.embedding.weight"], z,
+                                            None if gt_indices is None else gt_indices[k], lq)  # :339-342
+            if not use_quantize:
+                zq = z                                     # :349-350
+            aq = zq                                        # CombineQuantBlock, fema_utils.py:92-99
+            if prev_quant is not None:
+                aq = torch.cat((zq, F.interpolate(prev_quant, zq.shape[2:])), dim=1)
+            t = _conv(sd, f"after_quant_group.{k}.conv", aq)
+            if taps is not None and k == 0:
+                taps.update(z=z, zq=zq, after_quant=t)
+            losses.append(loss)
+            indices.append(idx)
+            k += 1
+            prev_quant = zq
+        elif lq and use_residual:
+            t = t + feats[i]                               # :361-362
         t = decoder_block(sd, f"decoder_group.{i}", t)
+        prev_dec = t
         if taps is not None:
             taps[f"dec{i}"] = t
     out = _conv(sd, "out_conv", t)                         # :369
-    return out, loss, loss * 0, [idx]
+    loss = sum(losses)                                     # :371
+    return out, loss, loss * 0, indices
 
 
 def decode_indices(sd: SD, indices: Tensor) -> Tensor:

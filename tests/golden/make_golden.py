@@ -37,6 +37,15 @@ CASES = [
     # scale 1 = the HQ autoencoder (LQ_stage=False)
     ("hq_e512_fwd", 1, 512, "perturbed", 18, "forward", (1, 3, 64, 96), {}),
     ("hq_e256_test", 1, 256, "default", 19, "test", (1, 3, 40, 72), {}),
+    # multi-scale codebooks (femasr_arch.py:280-299, 329-359): extra = codebook_params rows
+    ("x4_ms2_fwd", 4, 256, "perturbed", 20, "forward", (1, 3, 32, 32), {"codebooks": [[32, 1024, 256], [64, 512, 128]]}),
+    ("x2_ms3_fwd", 2, 256, "perturbed", 21, "forward", (1, 3, 64, 64),
+     {"codebooks": [[32, 512, 256], [64, 512, 256], [128, 256, 128]]}),
+    ("hq_ms2_fwd", 1, 256, "default", 22, "forward", (1, 3, 64, 64), {"codebooks": [[32, 1024, 256], [128, 256, 64]]}),
+    # gt_indices loss branch (femasr_arch.py:70-78, 84-90): forward(input, gt_indices=[...])
+    ("x4_e256_gt_fwd", 4, 256, "perturbed", 23, "forward", (2, 3, 32, 32), {"gt": True}),
+    ("x4_ms2_gt_fwd", 4, 256, "perturbed", 24, "forward", (1, 3, 32, 32),
+     {"codebooks": [[32, 1024, 256], [64, 512, 128]], "gt": True}),
 ]
 
 
@@ -56,12 +65,19 @@ def sample(t: torch.Tensor) -> np.ndarray:
 def main():
     ref = import_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    only = set(sys.argv[1:])
     for name, scale, e_dim, init, seed, entry, shape, extra in CASES:
-        sd = random_state_dict(scale, e_dim, seed=seed, init=init)
-        net = ref.FeMaSRNet(codebook_params=[[32, 1024, e_dim]], LQ_stage=scale != 1, scale_factor=scale).eval()
+        if only and name not in only:
+            continue
+        extra = dict(extra)
+        cbs = extra.pop("codebooks", [[32, 1024, e_dim]])
+        use_gt = extra.pop("gt", False)
+        sd = random_state_dict(scale, e_dim, seed=seed, init=init, codebooks=cbs)
+        net = ref.FeMaSRNet(codebook_params=cbs, LQ_stage=scale != 1, scale_factor=scale).eval()
         net.load_state_dict(sd, strict=True)
         g = torch.Generator().manual_seed(1000 + seed)
-        rec = dict(scale=scale, e_dim=e_dim, init=init, seed=seed, entry=entry, digest=sd_digest(sd))
+        rec = dict(scale=scale, e_dim=e_dim, init=init, seed=seed, entry=entry, digest=sd_digest(sd),
+                   codebooks=np.array(cbs, dtype=np.int64))
         rec.update({f"arg_{k}": v for k, v in extra.items()})
         taps = {}
         d = encode_depth(scale)
@@ -79,6 +95,8 @@ def main():
             hooks.append(enc.blocks[d + 1].register_forward_hook(hook("up1")))
             hooks.append(enc.blocks[d + 2].register_forward_hook(hook("up2")))
         hooks.append(net.before_quant_group[0].register_forward_hook(hook("z")))
+        for k in range(1, len(cbs)):
+            hooks.append(net.before_quant_group[k].register_forward_hook(hook(f"z{k}")))
         hooks.append(net.after_quant_group[0].register_forward_hook(hook("after_quant")))
         for i in range(3):
             hooks.append(net.decoder_group[i].register_forward_hook(hook(f"dec{i}")))
@@ -89,8 +107,15 @@ def main():
             else:
                 x = torch.rand(shape, generator=g)
                 if entry == "forward":
-                    out, loss, sem, idx = net(x)
+                    gt = None
+                    if use_gt:          # random "HQ codes" of the right shapes
+                        hb = shape[2] * scale // 8
+                        gt = [torch.randint(0, n, (shape[0], 1, hb * s // 32, shape[3] * scale // 8 * s // 32), generator=g)
+                              for s, n, _ in cbs]
+                        rec.update({f"gt_indices{k}": v.numpy() for k, v in enumerate(gt)})
+                    out, loss, sem, idx = net(x, gt) if use_gt else net(x)
                     rec.update(loss=loss.numpy(), sem=sem.numpy(), indices=idx[0].numpy())
+                    rec.update({f"indices{k}": v.numpy() for k, v in enumerate(idx) if k > 0})
                 elif entry == "test":
                     out = net.test(x)
                 else:

@@ -1,17 +1,13 @@
 """CPU: the oracle restatement reproduces the reference's outputs stored in tests/golden/*.npz
 (generated from the UNMODIFIED reference by tests/golden/make_golden.py)."""
-import glob
 import hashlib
-import os
 
 import numpy as np
 import pytest
 import torch
 
-from femasr_b200.spec import random_state_dict
 from oracle import femasr_oracle as O
-
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+from tests.golden_util import GOLDEN, IDS, gt_indices_of, indices_of, load_case
 
 
 def digest(sd):
@@ -22,31 +18,29 @@ def digest(sd):
     return h.hexdigest()
 
 
-def load_case(path):
-    g = np.load(path)
-    sd = random_state_dict(int(g["scale"]), int(g["e_dim"]), seed=int(g["seed"]), init=str(g["init"]))
-    return g, sd
-
-
 def sample(t):
     return t[:, ::17, ::3, ::3].contiguous().numpy()
 
 
 def test_golden_present():
-    assert len(GOLDEN) >= 9
+    assert len(GOLDEN) >= 14
 
 
-@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+@pytest.mark.parametrize("path", GOLDEN, ids=IDS)
 def test_oracle_matches_reference_golden(path):
-    g, sd = load_case(path)
+    g, sd, cbs = load_case(path)
     assert digest(sd) == str(g["digest"]), "seeded weight generator drifted from the one used for the goldens"
     scale, entry = int(g["scale"]), str(g["entry"])
     x = torch.from_numpy(g["input"])
     with torch.no_grad():
         if entry == "forward":
             taps = {}
-            out, loss, sem, idx = O.encode_and_decode(sd, x, scale, taps)
-            assert np.array_equal(idx[0].numpy(), g["indices"]), "codebook indices must be bit-exact"
+            out, loss, sem, idx = O.encode_and_decode(sd, x, scale, taps, cb_scales=[c[0] for c in cbs],
+                                                      gt_indices=gt_indices_of(g))
+            want_idx = indices_of(g)
+            assert len(idx) == len(want_idx) == len(cbs)
+            for a, b in zip(idx, want_idx):
+                assert np.array_equal(a.numpy(), b), "codebook indices must be bit-exact"
             np.testing.assert_allclose(loss.numpy(), g["loss"], rtol=1e-6)
             assert float(sem) == 0.0
             pairs = (("enc0", "swin"), ("enc1", "up1"), ("enc2", "up2"), ("z", "z"),
