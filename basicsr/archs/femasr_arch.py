@@ -7,10 +7,11 @@ and return tuples.  The module only HOLDS the parameters (so `.to()`, `.eval()`,
 decode_indices runs in libfemasr_b200.so (hand-written sm_100a CUDA) through `femasr_b200.net`.
 There is no CPU or eager-PyTorch fallback: calling the network without a CUDA sm_100 device raises.
 
-In scope: norm_type 'gn', act_type 'silu', one codebook at scale 32; LQ_stage=True with scale_factor 2 or 4 (the SR
-network) and LQ_stage=False (the HQ autoencoder that produces gt_indices / codebook visualisations); inference only
-(no autograd through the engine).  Anything else raises
-NotImplementedError at construction instead of silently computing something different.
+In scope: norm_type 'gn', act_type 'silu'; one codebook at scale 32 or the multi-scale variant with further codebooks
+at 64 / 128 (femasr_arch.py:280-299); LQ_stage=True with scale_factor 2 or 4 (the SR network) and LQ_stage=False (the
+HQ autoencoder that produces gt_indices / codebook visualisations); the gt_indices loss value (femasr_arch.py:84-90);
+inference only (no autograd through the engine).  Anything else raises NotImplementedError at construction instead of
+silently computing something different.
 """
 from __future__ import annotations
 
@@ -22,7 +23,7 @@ from torch import nn
 
 from basicsr.utils.registry import ARCH_REGISTRY
 from femasr_b200.net import NativeNet
-from femasr_b200.spec import param_spec, relative_position_index, shift_attn_mask
+from femasr_b200.spec import normalize_codebooks, param_spec, relative_position_index, shift_attn_mask
 
 
 class _Node(nn.Module):
@@ -72,8 +73,12 @@ class FeMaSRNet(nn.Module):
         if cb.ndim != 2 or cb.shape[1] != 3:
             raise ValueError("codebook_params must be [[scale, n_e, e_dim], ...]")
         unsupported = []
-        if cb.shape[0] != 1 or int(cb[0, 0]) != 32:
-            unsupported.append("multi-scale codebooks / codebook scale != 32")
+        try:
+            self.codebooks = normalize_codebooks(cb.tolist())
+            if len(self.codebooks) > 3 or any(n % 64 or e % 64 for _s, n, e in self.codebooks):
+                unsupported.append("codebook sizes / dims that are not multiples of 64")
+        except NotImplementedError as ex:
+            unsupported.append(str(ex))
         if norm_type != 'gn' or act_type != 'silu':
             unsupported.append(f"norm_type={norm_type!r}/act_type={act_type!r}")
         if (LQ_stage and scale_factor not in (2, 4)) or gt_resolution != 256 or in_channel != 3:
@@ -95,13 +100,14 @@ class FeMaSRNet(nn.Module):
         self.max_depth = int(np.log2(gt_resolution // self.codebook_scale[0]))
         self.gemm_path = int(ignore_kwargs.get("gemm_path", -1))    # -1: engine default
 
-        for name, shape, kind, fan_in in param_spec(self.scale_factor, self.e_dim, self.n_e, in_channel):
+        for name, shape, kind, fan_in in param_spec(self.scale_factor, self.e_dim, self.n_e, in_channel,
+                                                    codebooks=self.codebooks):
             if kind == "rpi":
                 _attach(self, name, relative_position_index(), buffer=True)
             elif kind == "mask":
                 _attach(self, name, shift_attn_mask(32, 32), buffer=True)
             else:
-                _attach(self, name, _init_tensor(shape, kind, fan_in, self.n_e), buffer=False)
+                _attach(self, name, _init_tensor(shape, kind, fan_in, fan_in), buffer=False)   # codebook: fan_in = its n_e
         self._engine = None
         self._engine_sig = None
 
@@ -121,7 +127,7 @@ class FeMaSRNet(nn.Module):
         if self._engine is None:
             gp = self.gemm_path if self.gemm_path >= 0 else default_gemm_path()
             self._engine = NativeNet(self.scale_factor, self.n_e, self.e_dim, self.use_quantize,
-                                     self.use_residual, gemm_path=gp)
+                                     self.use_residual, gemm_path=gp, codebooks=self.codebooks)
         if sig != self._engine_sig:
             self._engine.load_state_dict(params, device)
             self._engine_sig = sig
@@ -136,17 +142,17 @@ class FeMaSRNet(nn.Module):
 
     # ------------------------------------------------------------------ reference surface
     def encode_and_decode(self, input, gt_indices=None, current_iter=None):
-        """femasr_arch.py:311-374 -> (out_img, codebook_loss, semantic_loss, [indices])."""
-        if gt_indices is not None:
-            raise NotImplementedError("gt_indices (training supervision branch) is outside the inference hot path")
+        """femasr_arch.py:311-374 -> (out_img, codebook_loss, semantic_loss, [indices per codebook]).
+        ``gt_indices`` (list, one map per codebook) switches codebook_loss to the supervised form (:84-90); the value
+        is computed, no autograd graph is attached."""
         eng = self._native(input.device)
-        if eng.use_graph and input.is_cuda:
+        if eng.use_graph and input.is_cuda and gt_indices is None and len(self.codebooks) == 1:
             # fixed launch list replayed as a CUDA graph; results are copied out of the graph's static buffers so the
             # returned tensors stay valid across calls like the reference's
             out, loss, idx = (t.clone() for t in eng.forward_graph(input))
         else:
-            out, loss, idx = eng.forward(input)
-        return out, loss, loss * 0, [idx]
+            out, loss, idx = eng.forward(input, gt_indices=gt_indices)
+        return out, loss, loss * 0, (idx if isinstance(idx, list) else [idx])
 
     def decode_indices(self, indices):
         """femasr_arch.py:376-385."""

@@ -97,7 +97,11 @@ struct femasr_net {
   std::map<std::string, DevBuf> packed;   // K-major GEMM operand / expanded rel bias / codebook^T
   std::map<std::string, DevBuf> tcw;      // tensor-core operand (split fp16), gemm_path 1
   std::map<std::string, DevBuf> tcw_up;   // sub-pixel phase filters of the upsample-fused 3x3 convs
-  DevBuf esq;
+  std::map<std::string, DevBuf> esq;      // sum e^2 per codebook row, keyed by the codebook's parameter name
+  struct Codebook { int scale, n_e, e_dim; };
+  std::vector<Codebook> cbs;              // codebook_params rows; cbs[0].scale == 32
+  int level_cb[3] = {0, -1, -1};          // decoder level i (resolution 32 << i) -> codebook index or -1
+  int last_q_level = 0;                   // last decoder level that quantises (everything before it is index-critical)
   std::map<std::string, Tap> taps;
   int last_launches = 0;
   bool profile = false;
@@ -111,7 +115,7 @@ struct femasr_net {
     for (auto& kv : packed) cudaFree(kv.second.p);
     for (auto& kv : tcw) cudaFree(kv.second.p);
     for (auto& kv : tcw_up) cudaFree(kv.second.p);
-    cudaFree(esq.p);
+    for (auto& kv : esq) cudaFree(kv.second.p);
   }
 };
 
@@ -135,7 +139,7 @@ static void add_resblock(femasr_net* n, const std::string& p, int c) {
 }
 
 static void build_spec(femasr_net* n) {
-  const int scale = n->cfg.scale_factor, e = n->cfg.e_dim;
+  const int scale = n->cfg.scale_factor;
   const int d = n->depth;
   int res = 256 / scale;
   const std::string enc = "multiscale_encoder";
@@ -176,9 +180,14 @@ static void build_spec(femasr_net* n) {
     add_resblock(n, b + ".3", chan(r * 2));
   }
   add_conv(n, "out_conv", 64, 3, 3);
-  n->spec["quantize_group.0.embedding.weight"] = ParamInfo{(size_t)n->cfg.n_e * e, 3, n->cfg.n_e, e, 1};
-  add_conv(n, "before_quant_group.0", 256, e, 1);
-  add_conv(n, "after_quant_group.0.conv", e, 256, 3);
+  for (size_t k = 0; k < n->cbs.size(); ++k) {           // femasr_arch.py:280-299
+    const femasr_net::Codebook& cb = n->cbs[k];
+    const std::string ks = std::to_string(k);
+    const int ch = chan(cb.scale);
+    n->spec["quantize_group." + ks + ".embedding.weight"] = ParamInfo{(size_t)cb.n_e * cb.e_dim, 3, cb.n_e, cb.e_dim, 1};
+    add_conv(n, "before_quant_group." + ks, k == 0 ? ch : 2 * ch, cb.e_dim, 1);
+    add_conv(n, "after_quant_group." + ks + ".conv", k == 0 ? cb.e_dim : n->cbs[k - 1].e_dim + cb.e_dim, ch, 3);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -446,32 +455,130 @@ struct Ctx {
     ar.release(rs); ar.release(mu); ar.release(hid); ar.release(ao); ar.release(qkv); ar.release(T);
   }
 
-  // after_quant conv + 3 decoder blocks + out_conv.  x0in: [B,h,w,e] quantised features.
-  void decode(const float* zq, float* y_nchw, int B, int h, int w, const float* u1, const float* u2) {
-    const int e = net->cfg.e_dim;
-    float* x0 = ar.alloc((size_t)B * h * w * 256);
-    conv("after_quant_group.0.conv", zq, x0, B, h, w, e, 256, 3, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
-    tap("after_quant", x0, (size_t)B * h * w * 256);
-    float* d0 = up_block("decoder_group.0.block.1", "decoder_group.0.block.2", "decoder_group.0.block.3", x0, B, h, w, 256, 256, u1);
-    ar.release(x0);
-    tap("dec0", d0, (size_t)B * 2 * h * 2 * w * 256);
-    float* d1 = up_block("decoder_group.1.block.1", "decoder_group.1.block.2", "decoder_group.1.block.3", d0, B, 2 * h, 2 * w, 256, 128, u2);
-    ar.release(d0);
-    tap("dec1", d1, (size_t)B * 4 * h * 4 * w * 128);
-    float* d2 = up_block("decoder_group.2.block.1", "decoder_group.2.block.2", "decoder_group.2.block.3", d1, B, 4 * h, 4 * w, 128, 64, nullptr);
-    ar.release(d1);
-    tap("dec2", d2, (size_t)B * 8 * h * 8 * w * 64);
+  // One quantiser (femasr_arch.py:337-342 + VectorQuantizer.forward :50-100): z = before_quant(src) [N,e], argmin over
+  // codebook k, zq = z + (E[idx] - z); loss terms accumulate into cb_loss.  Returns z and zq (caller releases both).
+  void quantise(int k, const float* src, int Cin, int B, int hh, int ww, int64_t* indices, float* cb_loss,
+                const int64_t* gt, float** z_out, float** zq_out) {
+    const femasr_net::Codebook& cb = net->cbs[k];
+    const std::string ks = std::to_string(k);
+    const size_t N = (size_t)B * hh * ww;
+    const int e = cb.e_dim;
+    float* z = ar.alloc(N * e);
+    conv("before_quant_group." + ks, src, z, B, hh, ww, Cin, e, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
+    tap(k == 0 ? "z" : (k == 1 ? "z1" : "z2"), z, N * e);
+    float* zc = ar.alloc(N * cb.n_e);
+    conv("quantize_group." + ks + ".embedding", z, zc, B, hh, ww, e, cb.n_e, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, false);
+    float* zq = ar.alloc(N * e);
+    float* lrows = ar.alloc(N);
+    const bool gt_loss = gt && !net->hq;                 // :84: only the LQ stage uses gt_indices for the loss
+    float *zq_gt = nullptr, *gpart = nullptr;
+    const int gtiles = femasr_gram_diff_tiles(e);
+    if (gt_loss) { zq_gt = ar.alloc(N * e); gpart = ar.alloc((size_t)B * gtiles); }
+    if (!dry() && ok()) {
+      const std::string cname = "quantize_group." + ks + ".embedding.weight";
+      const float* cbw = net->raw[cname].p;
+      const float* esq = net->esq[cname].p;
+      run("vq_select", 0.0, [&] { return femasr_vq_select(z, zc, cbw, esq, indices, zq, lrows, (int)N, cb.n_e, e, 0, st); });
+      if (cb_loss && !gt_loss) {
+        const double s = 1.25 / ((double)N * e);         // q_latent + 0.25 * e_latent, :92
+        run("sum_scaled", 0.0, [&] { return k == 0 ? femasr_sum_scaled(lrows, cb_loss, N, s, st) : femasr_sum_scaled_add(lrows, cb_loss, N, s, st); });
+      } else if (cb_loss) {
+        run("vq_gt_rows", 0.0, [&] { return femasr_vq_gt_rows(z, cbw, gt, zq_gt, lrows, (int)N, cb.n_e, e, st); });
+        const double s = 0.25 / ((double)N * e);         // beta * mean((z_q_gt - z)^2), :87
+        run("sum_scaled", 0.0, [&] { return k == 0 ? femasr_sum_scaled(lrows, cb_loss, N, s, st) : femasr_sum_scaled_add(lrows, cb_loss, N, s, st); });
+        run("gram_diff", 4.0 * B * (double)hh * ww * e * e, [&] { return femasr_gram_diff(z, zq_gt, gpart, B, hh * ww, e, st); });
+        run("sum_scaled", 0.0, [&] { return femasr_sum_scaled_add(gpart, cb_loss, (size_t)B * gtiles, 1.0 / ((double)B * e * e), st); });
+      }
+    }
+    if (gt_loss) { ar.release(gpart); ar.release(zq_gt); }
+    ar.release(lrows);
+    ar.release(zc);
+    if (k == 0) tap("zq", zq, N * e);
+    *z_out = z; *zq_out = zq;
+  }
+
+  // The decoder loop of encode_and_decode (femasr_arch.py:327-369) from decoder level 0 on.
+  //   feats[i]   enc_feats[i] (NHWC, level i = resolution 32 << i) or nullptr when that level needs none
+  //   zq0_given  decode_indices: the gathered codebook-0 entries; no quantiser runs at any level (:376-385)
+  void decode_loop(const float* const* feats, const float* zq0_given, float* y_nchw, int64_t* indices, float* cb_loss,
+                   const int64_t* gt, int B, int h, int w) {
+    const femasr_net_config& cfg = net->cfg;
+    const bool lq = !net->hq;
+    float* t = nullptr;                       // decoder stream
+    float* prev_q = nullptr; int pq_h = 0, pq_w = 0, pq_e = 0;   // previous z_quant (:358)
+    float* prev_z = nullptr;
+    size_t idx_off = 0;
+    int Cprev = 0;                            // channels of t
+    for (int i = 0; i < 3; ++i) {
+      const int hh = h << i, ww = w << i, ch = chan(32 << i), co = chan(64 << i);
+      const int k = zq0_given ? (i == 0 ? 0 : -1) : net->level_cb[i];
+      if (k >= 0) {
+        const femasr_net::Codebook& cb = net->cbs[k];
+        const size_t N = (size_t)B * hh * ww;
+        const float* aq = zq0_given;
+        float *z = nullptr, *zq = nullptr;
+        if (!zq0_given) {
+          precise_region = true;
+          const float* src = feats[i];
+          float* cat = nullptr;
+          int Cin = ch;
+          if (t) {                            // cat(enc_feats[i], prev_dec_feat), :332-333
+            cat = ar.alloc(N * 2 * ch);
+            if (!dry() && ok())
+              run("concat_channels", 0.0, [&] { return femasr_concat_channels(feats[i], ch, t, hh, ww, ch, cat, B, hh, ww, st); });
+            ar.release(t); t = nullptr;
+            src = cat; Cin = 2 * ch;
+          }
+          quantise(k, src, Cin, B, hh, ww, indices ? indices + idx_off : nullptr, cb_loss,
+                   gt ? gt + idx_off : nullptr, &z, &zq);
+          idx_off += N;
+          if (cat) ar.release(cat);
+          aq = cfg.use_quantize ? zq : z;     // :349-350
+          if (i >= net->last_q_level) precise_region = false;
+        }
+        int e_in = cb.e_dim;
+        float* cat2 = nullptr;
+        if (prev_q) {                         // CombineQuantBlock: cat(z_quant, interpolate(prev_quant)), fema_utils.py:92-99
+          cat2 = ar.alloc(N * (cb.e_dim + pq_e));
+          const float* a0 = aq; const int pe = pq_e, ph = pq_h, pw = pq_w; const float* pq = prev_q;
+          if (!dry() && ok())
+            run("concat_channels", 0.0, [&] { return femasr_concat_channels(a0, cb.e_dim, pq, ph, pw, pe, cat2, B, hh, ww, st); });
+          aq = cat2; e_in += pq_e;
+        }
+        t = ar.alloc(N * ch);
+        conv("after_quant_group." + std::to_string(k) + ".conv", aq, t, B, hh, ww, e_in, ch, 3, 1, 0, FEMASR_PRO_NONE,
+             nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
+        if (k == 0) tap("after_quant", t, N * ch);
+        if (cat2) ar.release(cat2);
+        if (prev_q) { ar.release(prev_q); ar.release(prev_z); }
+        if (!zq0_given) {                     // prev_quant_feat = z_quant (after the use_quantize override), :358
+          prev_q = cfg.use_quantize ? zq : z; prev_z = cfg.use_quantize ? z : zq;
+          pq_h = hh; pq_w = ww; pq_e = cb.e_dim;
+        }
+      }
+      (void)Cprev;
+      // the skip add of the NEXT level (x = x + enc_feats[i+1], :361-362) rides on this block's last epilogue
+      const bool next_quant = i + 1 < 3 && !zq0_given && net->level_cb[i + 1] >= 0;
+      const float* extra = (i + 1 < 3 && !zq0_given && lq && cfg.use_residual && !next_quant) ? feats[i + 1] : nullptr;
+      const std::string b = "decoder_group." + std::to_string(i) + ".block";
+      float* nt = up_block(b + ".1", b + ".2", b + ".3", t, B, hh, ww, ch, co, extra);
+      ar.release(t);
+      t = nt;
+      tap(i == 0 ? "dec0" : (i == 1 ? "dec1" : "dec2"), t, (size_t)B * 2 * hh * 2 * ww * co);
+    }
+    if (prev_q) { ar.release(prev_q); ar.release(prev_z); }
     {
       const float *ow = P("out_conv.weight"), *ob = P("out_conv.bias");
+      const float* d2 = t;
       run("out_conv", 2.0 * 9 * 64 * 3 * (double)B * 64 * h * w,
           [&] { return femasr_out_conv3x3(d2, ow, ob, y_nchw, B, 8 * h, 8 * w, 64, st); });
     }
-    ar.release(d2);
+    ar.release(t);
   }
 
-  void forward(const float* x_nchw, float* y_nchw, int64_t* indices, float* cb_loss, int B, int H, int W) {
+  void forward(const float* x_nchw, float* y_nchw, int64_t* indices, float* cb_loss, const int64_t* gt, int B, int H, int W) {
     const femasr_net_config& cfg = net->cfg;
-    const int d = net->depth, e = cfg.e_dim;
+    const int d = net->depth;
     const std::string enc = "multiscale_encoder";
     int c = chan(256 / cfg.scale_factor);
     int h = H - 1, w = W - 1;
@@ -496,6 +603,12 @@ struct Ctx {
       const int c0 = c;
       run("in_conv", in_flops, [&] { return femasr_in_conv4x4_split(x_nchw, iw, ib, in_hi, in_lo, B, cfg.in_channel, H, W, c0, st); });
     }
+    // which enc_feats the decoder loop reads: at quantising levels (before_quant input) and, in the LQ stage with
+    // use_residual, at the other levels > 0 (skip adds)
+    bool need[3];
+    for (int i = 0; i < 3; ++i)
+      need[i] = net->level_cb[i] >= 0 || (i > 0 && !net->hq && cfg.use_residual);
+    float* feats[3] = {nullptr, nullptr, nullptr};
     for (int i = 0; i < d; ++i) {
       const std::string b = enc + ".blocks." + std::to_string(i);
       const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1, co = chan((256 / cfg.scale_factor) >> (i + 1));
@@ -509,7 +622,8 @@ struct Ctx {
         conv(b + ".0", cur, nxt, B, h, w, c, co, 3, 2, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
       }
       if (i == 0 && in_lo) { ar.release(in_lo); ar.release(in_hi); in_lo = in_hi = nullptr; }
-      if (cur) ar.release(cur);
+      // HQ stage: enc_feats = the down blocks' outputs reversed (:316); block i-1's output is level d-i
+      if (cur) { if (net->hq && i > 0 && need[d - i]) feats[d - i] = cur; else ar.release(cur); }
       cur = nxt; h = ho; w = wo; c = co;
       Stats sd = resblock(b + ".1", cur, B, h, w, c, nullptr, sd0, true);
       resblock(b + ".2", cur, B, h, w, c, nullptr, sd, false);
@@ -517,51 +631,34 @@ struct Ctx {
     tap("down", cur, (size_t)B * h * w * c);
     if (!net->hq) swin(enc + ".blocks." + std::to_string(d), cur, B, h, w);
     tap("swin", cur, (size_t)B * h * w * c);
-    float *u1 = nullptr, *u2 = nullptr;
-    precise_region = false;        // the up branches only reach the decoder's skip adds (femasr_arch.py:313-314)
-    if (cfg.use_residual && !net->hq) {
+    feats[0] = cur;
+    // the up branches reach the decoder's skip adds (femasr_arch.py:361-362) and, in multi-scale nets, the later quantisers
+    precise_region = net->last_q_level >= 1;
+    if (!net->hq && (need[1] || need[2])) {
       const std::string b1 = enc + ".blocks." + std::to_string(d + 1), b2 = enc + ".blocks." + std::to_string(d + 2);
-      u1 = up_block(b1 + ".1", b1 + ".2", b1 + ".3", cur, B, h, w, 256, 256, nullptr);
-      tap("up1", u1, (size_t)B * 2 * h * 2 * w * 256);
-      u2 = up_block(b2 + ".1", b2 + ".2", b2 + ".3", u1, B, 2 * h, 2 * w, 256, 128, nullptr);
-      tap("up2", u2, (size_t)B * 4 * h * 4 * w * 128);
+      feats[1] = up_block(b1 + ".1", b1 + ".2", b1 + ".3", cur, B, h, w, 256, 256, nullptr);
+      tap("up1", feats[1], (size_t)B * 2 * h * 2 * w * 256);
+      if (need[2]) {
+        precise_region = net->last_q_level >= 2;
+        feats[2] = up_block(b2 + ".1", b2 + ".2", b2 + ".3", feats[1], B, 2 * h, 2 * w, 256, 128, nullptr);
+        tap("up2", feats[2], (size_t)B * 4 * h * 4 * w * 128);
+      }
     }
-    // feature matching
-    precise_region = true;
-    const size_t N = (size_t)B * h * w;
-    float* z = ar.alloc(N * e);
-    conv("before_quant_group.0", cur, z, B, h, w, 256, e, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
-    ar.release(cur);
-    tap("z", z, N * e);
-    float* zc = ar.alloc(N * cfg.n_e);
-    conv("quantize_group.0.embedding", z, zc, B, h, w, e, cfg.n_e, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, false);
-    float* zq = ar.alloc(N * e);
-    float* lrows = ar.alloc(N);
-    if (!dry() && ok()) {
-      const float* cbw = net->raw["quantize_group.0.embedding.weight"].p;
-      run("vq_select", 0.0, [&] { return femasr_vq_select(z, zc, cbw, net->esq.p, indices, zq, lrows, (int)N, cfg.n_e, e, 0, st); });
-      if (cb_loss) run("sum_scaled", 0.0, [&] { return femasr_sum_scaled(lrows, cb_loss, N, 1.25 / ((double)N * e), st); });
-    }
-    ar.release(lrows);
-    ar.release(zc);
-    tap("zq", zq, N * e);
     precise_region = false;
-    decode(cfg.use_quantize ? zq : z, y_nchw, B, h, w, u1, u2);
-    if (u2) ar.release(u2);
-    if (u1) ar.release(u1);
-    ar.release(zq);
-    ar.release(z);
+    decode_loop(feats, nullptr, y_nchw, indices, cb_loss, gt, B, h, w);
+    for (int i = 2; i >= 0; --i) if (feats[i]) ar.release(feats[i]);
   }
 
   void decode_indices(const int64_t* idx, float* y_nchw, int B, int h, int w) {
-    const int e = net->cfg.e_dim;
+    const femasr_net::Codebook& cb = net->cbs[0];
     const size_t N = (size_t)B * h * w;
-    float* zq = ar.alloc(N * e);
+    float* zq = ar.alloc(N * cb.e_dim);
     if (!dry() && ok()) {
       const float* cbw = net->raw["quantize_group.0.embedding.weight"].p;
-      run("codebook_gather", 0.0, [&] { return femasr_codebook_gather(idx, cbw, zq, (int)N, net->cfg.n_e, e, st); });
+      run("codebook_gather", 0.0, [&] { return femasr_codebook_gather(idx, cbw, zq, (int)N, cb.n_e, cb.e_dim, st); });
     }
-    decode(zq, y_nchw, B, h, w, nullptr, nullptr);
+    const float* none[3] = {nullptr, nullptr, nullptr};
+    decode_loop(none, zq, y_nchw, nullptr, nullptr, nullptr, B, h, w);
     ar.release(zq);
   }
 };
@@ -584,7 +681,7 @@ static int check_geometry(femasr_net* net, int B, int H, int W) {
 }  // namespace femasr
 
 extern "C" const char* femasr_last_error(void) { return g_err.c_str(); }
-extern "C" int femasr_abi_version(void) { return 1; }
+extern "C" int femasr_abi_version(void) { return 2; }
 
 extern "C" int femasr_device_cc(void) {
   int dev = 0;
@@ -599,11 +696,29 @@ extern "C" int femasr_net_create(const femasr_net_config* cfg, femasr_net** out)
   FEMASR_CHECK_ARG(cfg->scale_factor == 1 || cfg->scale_factor == 2 || cfg->scale_factor == 4,
                    "net_create: scale_factor must be 4, 2 (LQ stage) or 1 (HQ autoencoder stage)");
   FEMASR_CHECK_ARG(cfg->in_channel == 3, "net_create: in_channel must be 3");
-  FEMASR_CHECK_ARG(cfg->e_dim > 0 && cfg->e_dim % 64 == 0 && cfg->e_dim <= 1024, "net_create: e_dim must be a multiple of 64");
-  FEMASR_CHECK_ARG(cfg->n_e > 0 && cfg->n_e % 64 == 0, "net_create: n_e must be a multiple of 64");
   FEMASR_CHECK_ARG(cfg->gemm_path == 0 || cfg->gemm_path == 1, "net_create: gemm_path must be 0 or 1");
+  FEMASR_CHECK_ARG(cfg->n_codebooks >= 0 && cfg->n_codebooks <= FEMASR_MAX_CODEBOOKS, "net_create: at most 3 codebooks");
+  std::vector<femasr_net::Codebook> cbs;
+  if (cfg->n_codebooks <= 1 && !(cfg->n_codebooks == 1 && cfg->cb_scale[0]))
+    cbs.push_back({32, cfg->n_e, cfg->e_dim});
+  else
+    for (int k = 0; k < cfg->n_codebooks; ++k) cbs.push_back({cfg->cb_scale[k], cfg->cb_n_e[k], cfg->cb_e_dim[k]});
+  FEMASR_CHECK_ARG(cbs[0].scale == 32, "net_create: the first codebook must be at scale 32 (femasr_arch.py:255-256)");
+  for (size_t k = 0; k < cbs.size(); ++k) {
+    FEMASR_CHECK_ARG(cbs[k].e_dim > 0 && cbs[k].e_dim % 64 == 0 && cbs[k].e_dim <= 1024, "net_create: e_dim must be a multiple of 64");
+    FEMASR_CHECK_ARG(cbs[k].n_e > 0 && cbs[k].n_e % 64 == 0, "net_create: n_e must be a multiple of 64");
+    FEMASR_CHECK_ARG(k == 0 || ((cbs[k].scale == 64 || cbs[k].scale == 128) && cbs[k].scale > cbs[k - 1].scale),
+                     "net_create: further codebooks must sit at increasing scales out of 64, 128");
+  }
   femasr_net* n = new femasr_net();
   n->cfg = *cfg;
+  n->cfg.n_e = cbs[0].n_e; n->cfg.e_dim = cbs[0].e_dim;
+  n->cbs = cbs;
+  for (size_t k = 0; k < cbs.size(); ++k) {
+    const int lvl = cbs[k].scale == 32 ? 0 : (cbs[k].scale == 64 ? 1 : 2);
+    n->level_cb[lvl] = (int)k;
+    n->last_q_level = lvl;
+  }
   n->depth = cfg->scale_factor == 4 ? 1 : (cfg->scale_factor == 2 ? 2 : 3);
   n->hq = cfg->scale_factor == 1;
   if (const char* ev = getenv("FEMASR_TC_PRECISE")) n->tc_precise = atoi(ev) != 0;
@@ -664,8 +779,9 @@ extern "C" int femasr_net_set_param(femasr_net* net, const char* name, const flo
     if (!pb.p) { FEMASR_CUDA(cudaMalloc(&pb.p, numel * sizeof(float))); pb.n = numel; }
     int s = femasr_pack_weight(rb.p, pb.p, pi.Cout, pi.Cin, 1, 1, st);
     if (s) return s;
-    if (!net->esq.p) { FEMASR_CUDA(cudaMalloc(&net->esq.p, pi.Cout * sizeof(float))); net->esq.n = pi.Cout; }
-    return femasr_row_sumsq(rb.p, net->esq.p, pi.Cout, pi.Cin, st);
+    DevBuf& eb = net->esq[key];
+    if (!eb.p) { FEMASR_CUDA(cudaMalloc(&eb.p, pi.Cout * sizeof(float))); eb.n = pi.Cout; }
+    return femasr_row_sumsq(rb.p, eb.p, pi.Cout, pi.Cin, st);
   }
   return FEMASR_OK;
 }
@@ -682,13 +798,20 @@ extern "C" int femasr_net_workspace_bytes(femasr_net* net, int B, int H, int W, 
   int s = check_geometry(net, B, H, W);
   if (s) return s;
   Ctx c; c.net = net; c.st = nullptr; c.ar.dry = true; c.ar.base = reinterpret_cast<char*>(uintptr_t(1) << 40);
-  c.forward(nullptr, nullptr, nullptr, nullptr, B, H, W);
+  // sized for the gt_indices loss branch too (its scratch is small): one workspace serves forward and forward_gt
+  c.forward(nullptr, nullptr, nullptr, nullptr, reinterpret_cast<const int64_t*>(uintptr_t(8)), B, H, W);
   *bytes = c.ar.peak + 256;
   return c.status;
 }
 
 extern "C" int femasr_net_forward(femasr_net* net, const float* x, float* y, int64_t* indices, float* cb_loss, int B,
                                   int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
+  return femasr_net_forward_gt(net, x, y, indices, cb_loss, nullptr, B, H, W, workspace, workspace_bytes, stream);
+}
+
+extern "C" int femasr_net_forward_gt(femasr_net* net, const float* x, float* y, int64_t* indices, float* cb_loss,
+                                     const int64_t* gt_indices, int B, int H, int W, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
   FEMASR_CHECK_ARG(net && x && y && workspace, "forward: null pointer");
   int s = check_geometry(net, B, H, W);
   if (s) return s;
@@ -702,7 +825,7 @@ extern "C" int femasr_net_forward(femasr_net* net, const float* x, float* y, int
   Ctx c; c.net = net; c.st = as_stream(stream); c.ar.dry = false;
   c.ar.base = reinterpret_cast<char*>(workspace) + mis; c.ar.cap = workspace_bytes - mis;
   const long l0 = g_launches;
-  c.forward(x, y, indices, cb_loss, B, H, W);
+  c.forward(x, y, indices, cb_loss, gt_indices, B, H, W);
   net->last_launches = (int)(g_launches - l0);
   return c.status;
 }
@@ -735,7 +858,7 @@ extern "C" int femasr_net_decode_indices(femasr_net* net, const int64_t* indices
 
 extern "C" int femasr_net_set_tap(femasr_net* net, const char* stage, float* dst, size_t capacity) {
   FEMASR_CHECK_ARG(net && stage, "set_tap: null pointer");
-  static const char* names[] = {"in_conv", "down", "swin", "up1", "up2", "z", "zq", "after_quant", "dec0", "dec1", "dec2"};
+  static const char* names[] = {"in_conv", "down", "swin", "up1", "up2", "z", "zq", "after_quant", "dec0", "dec1", "dec2", "z1", "z2"};
   bool known = false;
   for (const char* n : names) known = known || strcmp(n, stage) == 0;
   if (!known) return fail(FEMASR_ERR_ARG, std::string("set_tap: unknown stage ") + stage);
@@ -782,7 +905,7 @@ extern "C" const char* femasr_net_profile_json(femasr_net* net) {
 
 extern "C" double femasr_net_flops(femasr_net* net, int B, int H, int W) {
   if (!net) return 0.0;
-  const int scale = net->cfg.scale_factor, d = net->depth, e = net->cfg.e_dim;
+  const int scale = net->cfg.scale_factor, d = net->depth;
   const double cin = chan(256 / scale);
   double f = 2.0 * 3 * 16 * cin * (H - 1) * (double)(W - 1);
   double ch = cin, hh = H, ww = W;
@@ -795,7 +918,12 @@ extern "C" double femasr_net_flops(femasr_net* net, int B, int H, int W) {
   const double px = hh * ww;
   const double lin = 2.0 * 256 * (768 + 256 + 1024 + 1024) * px, att = 2 * 2.0 * 64 * 256 * px;
   if (!net->hq) f += 4 * (6 * (lin + att) + 2.0 * 9 * 256 * 256 * px);
-  f += 2.0 * 256 * e * px + 2.0 * net->cfg.n_e * e * px + 2.0 * 9 * e * 256 * px;
+  for (size_t k = 0; k < net->cbs.size(); ++k) {      // before_quant 1x1, z.E^T, after_quant 3x3 at each codebook's level
+    const femasr_net::Codebook& cb = net->cbs[k];
+    const double m = cb.scale / 32.0, pk = px * m * m, chk = chan(cb.scale), e = cb.e_dim;
+    const double ein = k == 0 ? e : e + net->cbs[k - 1].e_dim;
+    f += 2.0 * (k == 0 ? chk : 2 * chk) * e * pk + 2.0 * cb.n_e * e * pk + 2.0 * 9 * ein * chk * pk;
+  }
   const double up[2][3] = {{256, 256, 2}, {256, 128, 4}};
   if (!net->hq) for (auto& u : up) f += (2.0 * 9 * u[0] * u[1] + 4 * 2.0 * 9 * u[1] * u[1]) * px * u[2] * u[2];
   const double dec[3][3] = {{256, 256, 2}, {256, 128, 4}, {128, 64, 8}};

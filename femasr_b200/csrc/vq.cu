@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(256) vq_select_kernel(const float* __restrict_
   if (lane == 0 && loss_rows) loss_rows[r] = l;
 }
 
+template <bool ACC>
 __global__ void __launch_bounds__(1024) sum_scaled_kernel(const float* __restrict__ x, float* __restrict__ out, size_t n,
                                                           double scale) {
   __shared__ double red[32];
@@ -68,7 +69,98 @@ __global__ void __launch_bounds__(1024) sum_scaled_kernel(const float* __restric
   __syncthreads();
   if (threadIdx.x < 32) {
     s = warp_sum_d(red[threadIdx.x]);
-    if (threadIdx.x == 0) out[0] = (float)(s * scale);
+    if (threadIdx.x == 0) out[0] = ACC ? (float)((double)out[0] + s * scale) : (float)(s * scale);
+  }
+}
+
+// out[B,H,W,Ca+Cb] = cat(a[B,H,W,Ca], nearest(b[B,Hb,Wb,Cb] -> H x W))  -- torch.cat along channels with
+// F.interpolate's default nearest mode (src = floor(dst * in / out)); femasr_arch.py:332-335, fema_utils.py:93-96.
+__global__ void __launch_bounds__(256) concat_channels_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                              float4* __restrict__ out, int H, int W, int Hb, int Wb,
+                                                              int ca4, int cb4, long total4) {
+  const long i = (long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = ca4 + cb4;
+  const int c = (int)(i % c4);
+  const long pix = i / c4;
+  if (c < ca4) { out[i] = __ldg(a + pix * ca4 + c); return; }
+  const int x = (int)(pix % W);
+  const long t = pix / W;
+  const int y = (int)(t % H);
+  const long bi = t / H;
+  const int ys = min((int)(((long)y * Hb) / H), Hb - 1), xs = min((int)(((long)x * Wb) / W), Wb - 1);
+  out[i] = __ldg(b + ((bi * Hb + ys) * Wb + xs) * cb4 + (c - ca4));
+}
+
+// gt_indices branch of the VQ loss (femasr_arch.py:70-78, 87-88): zq_gt[r] = codebook[gt[r]],
+// rows[r] = sum_k (zq_gt[r][k] - z[r][k])^2.  One warp per row.
+__global__ void __launch_bounds__(256) vq_gt_rows_kernel(const float* __restrict__ z, const float* __restrict__ codebook,
+                                                         const int64_t* __restrict__ gt, float* __restrict__ zq_gt,
+                                                         float* __restrict__ rows, int N, int n_e, int e_dim) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= N) return;
+  const int lane = threadIdx.x & 31;
+  long j = gt[r];
+  j = j < 0 ? 0 : (j >= n_e ? n_e - 1 : j);
+  float l = 0.f;
+  for (int k = lane; k < e_dim; k += 32) {
+    const float e = __ldg(codebook + j * e_dim + k);
+    const float d = __fsub_rn(e, z[(long)r * e_dim + k]);
+    l = fmaf(d, d, l);
+    zq_gt[(long)r * e_dim + k] = e;
+  }
+  l = warp_sum(l);
+  if (lane == 0) rows[r] = l;
+}
+
+// Gram-matrix texture loss (femasr_arch.py:40-48): per image G(x) = x^T x / HW over x [HW, C];
+// partial[b][tile] = sum over the 32x32 tile of (G(x) - G(y))^2.  256 threads, 2x2 outputs each, fp32 FMA.
+__global__ void __launch_bounds__(256) gram_diff_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                        float* __restrict__ partial, int HW, int C) {
+  __shared__ float xi[32][33], xj[32][33], yi[32][33], yj[32][33];
+  __shared__ float red[8];
+  const int tiles = C / 32;
+  const int b = blockIdx.y, ti = blockIdx.x / tiles, tj = blockIdx.x % tiles;
+  const float* xb = x + (long)b * HW * C;
+  const float* yb = y + (long)b * HW * C;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float ax[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, ay[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < HW; k0 += 32) {
+    for (int e = threadIdx.x; e < 1024; e += 256) {
+      const int kk = e >> 5, cc = e & 31;
+      const bool in = k0 + kk < HW;
+      const long row = (long)(k0 + kk) * C;
+      xi[kk][cc] = in ? xb[row + ti * 32 + cc] : 0.f;
+      xj[kk][cc] = in ? xb[row + tj * 32 + cc] : 0.f;
+      yi[kk][cc] = in ? yb[row + ti * 32 + cc] : 0.f;
+      yj[kk][cc] = in ? yb[row + tj * 32 + cc] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          ax[u][v] = fmaf(xi[kk][ty * 2 + u], xj[kk][tx * 2 + v], ax[u][v]);
+          ay[u][v] = fmaf(yi[kk][ty * 2 + u], yj[kk][tx * 2 + v], ay[u][v]);
+        }
+    }
+    __syncthreads();
+  }
+  const float inv = 1.0f / (float)HW;
+  float s = 0.f;
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int v = 0; v < 2; ++v) { const float d = ax[u][v] * inv - ay[u][v] * inv; s = fmaf(d, d, s); }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = 0.f;
+    for (int w = 0; w < 8; ++w) tsum += red[w];
+    partial[(long)b * gridDim.x + blockIdx.x] = tsum;
   }
 }
 
@@ -103,8 +195,42 @@ extern "C" int femasr_vq_select(const float* z, const float* zc, const float* co
 
 extern "C" int femasr_sum_scaled(const float* x, float* out, size_t n, double scale, void* stream) {
   FEMASR_CHECK_ARG(x && out && n > 0, "sum_scaled: bad argument");
-  sum_scaled_kernel<<<1, 1024, 0, as_stream(stream)>>>(x, out, n, scale);
+  sum_scaled_kernel<false><<<1, 1024, 0, as_stream(stream)>>>(x, out, n, scale);
   return launch_status("sum_scaled_kernel");
+}
+
+extern "C" int femasr_sum_scaled_add(const float* x, float* out, size_t n, double scale, void* stream) {
+  FEMASR_CHECK_ARG(x && out && n > 0, "sum_scaled_add: bad argument");
+  sum_scaled_kernel<true><<<1, 1024, 0, as_stream(stream)>>>(x, out, n, scale);
+  return launch_status("sum_scaled_kernel");
+}
+
+extern "C" int femasr_concat_channels(const float* a, int Ca, const float* b, int Hb, int Wb, int Cb, float* out, int B,
+                                      int H, int W, void* stream) {
+  FEMASR_CHECK_ARG(a && b && out && B > 0 && H > 0 && W > 0 && Hb > 0 && Wb > 0, "concat_channels: bad argument");
+  FEMASR_CHECK_ARG(Ca > 0 && Cb > 0 && Ca % 4 == 0 && Cb % 4 == 0, "concat_channels: channel counts must be multiples of 4");
+  const long total4 = (long)B * H * W * ((Ca + Cb) / 4);
+  concat_channels_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), reinterpret_cast<float4*>(out), H, W, Hb, Wb,
+      Ca / 4, Cb / 4, total4);
+  return launch_status("concat_channels_kernel");
+}
+
+extern "C" int femasr_vq_gt_rows(const float* z, const float* codebook, const int64_t* gt, float* zq_gt, float* rows,
+                                 int N, int n_e, int e_dim, void* stream) {
+  FEMASR_CHECK_ARG(z && codebook && gt && zq_gt && rows && N > 0 && n_e > 0 && e_dim > 0, "vq_gt_rows: bad argument");
+  vq_gt_rows_kernel<<<(N + 7) / 8, 256, 0, as_stream(stream)>>>(z, codebook, gt, zq_gt, rows, N, n_e, e_dim);
+  return launch_status("vq_gt_rows_kernel");
+}
+
+extern "C" int femasr_gram_diff_tiles(int C) { return C > 0 && C % 32 == 0 ? (C / 32) * (C / 32) : 0; }
+
+extern "C" int femasr_gram_diff(const float* x, const float* y, float* partial, int B, int HW, int C, void* stream) {
+  FEMASR_CHECK_ARG(x && y && partial && B > 0 && HW > 0, "gram_diff: bad argument");
+  FEMASR_CHECK_ARG(C > 0 && C % 32 == 0 && B <= 65535, "gram_diff: C must be a multiple of 32");
+  const dim3 grid((unsigned)femasr_gram_diff_tiles(C), (unsigned)B);
+  gram_diff_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, y, partial, HW, C);
+  return launch_status("gram_diff_kernel");
 }
 
 extern "C" int femasr_codebook_gather(const int64_t* idx, const float* codebook, float* zq, int N, int n_e, int e_dim,

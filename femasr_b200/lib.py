@@ -28,7 +28,8 @@ _I, _V, _Z, _D, _F = C.c_int, C.c_void_p, C.c_size_t, C.c_double, C.c_float
 
 class NetConfig(C.Structure):
     _fields_ = [("scale_factor", C.c_int), ("n_e", C.c_int), ("e_dim", C.c_int), ("in_channel", C.c_int),
-                ("use_quantize", C.c_int), ("use_residual", C.c_int), ("gemm_path", C.c_int)]
+                ("use_quantize", C.c_int), ("use_residual", C.c_int), ("gemm_path", C.c_int),
+                ("n_codebooks", C.c_int), ("cb_scale", C.c_int * 3), ("cb_n_e", C.c_int * 3), ("cb_e_dim", C.c_int * 3)]
 
 
 class IgemmArgs(C.Structure):
@@ -62,6 +63,7 @@ SIGNATURES = {
     "femasr_net_params_complete": (_I, [_V]),
     "femasr_net_workspace_bytes": (_I, [_V, _I, _I, _I, C.POINTER(_Z)]),
     "femasr_net_forward": (_I, [_V, _V, _V, _V, _V, _I, _I, _I, _V, _Z, _V]),
+    "femasr_net_forward_gt": (_I, [_V, _V, _V, _V, _V, _V, _I, _I, _I, _V, _Z, _V]),
     "femasr_net_decode_indices": (_I, [_V, _V, _V, _I, _I, _I, _V, _Z, _V]),
     "femasr_net_decode_workspace_bytes": (_I, [_V, _I, _I, _I, C.POINTER(_Z)]),
     "femasr_net_set_tap": (_I, [_V, C.c_char_p, _V, _Z]),
@@ -91,6 +93,11 @@ SIGNATURES = {
     "femasr_row_sumsq": (_I, [_V, _V, _I, _I, _V]),
     "femasr_vq_select": (_I, [_V, _V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _V]),
     "femasr_sum_scaled": (_I, [_V, _V, _Z, _D, _V]),
+    "femasr_sum_scaled_add": (_I, [_V, _V, _Z, _D, _V]),
+    "femasr_concat_channels": (_I, [_V, _I, _V, _I, _I, _I, _V, _I, _I, _I, _V]),
+    "femasr_vq_gt_rows": (_I, [_V, _V, _V, _V, _V, _I, _I, _I, _V]),
+    "femasr_gram_diff_tiles": (_I, [_I]),
+    "femasr_gram_diff": (_I, [_V, _V, _V, _I, _I, _I, _V]),
     "femasr_codebook_gather": (_I, [_V, _V, _V, _I, _I, _I, _V]),
     "femasr_in_conv4x4": (_I, [_V, _V, _V, _V, _I, _I, _I, _I, _I, _V]),
     "femasr_in_conv4x4_split": (_I, [_V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _V]),

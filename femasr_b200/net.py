@@ -16,7 +16,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import lib as L
-from .spec import param_spec
+from .spec import normalize_codebooks, param_spec
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -49,17 +49,23 @@ def padded_size(n: int, scale: int) -> int:
 
 class NativeNet:
     def __init__(self, scale_factor: int, n_e: int, e_dim: int, use_quantize: bool = True,
-                 use_residual: bool = True, gemm_path: int = 0):
+                 use_residual: bool = True, gemm_path: int = 0, codebooks=None):
+        """``codebooks``: the reference's ``codebook_params`` rows [[scale, n_e, e_dim], ...] for the multi-scale
+        variant (femasr_arch.py:231-235); default one codebook (32, n_e, e_dim)."""
         self.lib = L.load()
         self.scale = int(scale_factor)
-        self.n_e, self.e_dim = int(n_e), int(e_dim)
+        self.codebooks = normalize_codebooks(codebooks, n_e, e_dim)
+        self.n_e, self.e_dim = self.codebooks[0][1], self.codebooks[0][2]
+        K = len(self.codebooks)
+        pad = lambda v: (C.c_int * 3)(*(list(v) + [0] * (3 - K)))
         self.cfg = L.NetConfig(self.scale, self.n_e, self.e_dim, 3, int(bool(use_quantize)),
-                               int(bool(use_residual)), int(gemm_path))
+                               int(bool(use_residual)), int(gemm_path), K, pad([c[0] for c in self.codebooks]),
+                               pad([c[1] for c in self.codebooks]), pad([c[2] for c in self.codebooks]))
         self._h = C.c_void_p()
         self._ws: Optional[torch.Tensor] = None
         self._taps: Dict[str, torch.Tensor] = {}
         self.device: Optional[torch.device] = None
-        self.names = [n for (n, _s, kind, _f) in param_spec(self.scale, self.e_dim, self.n_e)
+        self.names = [n for (n, _s, kind, _f) in param_spec(self.scale, self.e_dim, self.n_e, codebooks=self.codebooks)
                       if kind not in ("rpi", "mask")]
         # the forward is a fixed launch list per input shape: replay it as a CUDA graph (no per-launch host work)
         self.use_graph = os.environ.get("FEMASR_CUDA_GRAPH", "1") != "0"
@@ -119,10 +125,18 @@ class NativeNet:
         return self._ws
 
     # ------------------------------------------------------------------ graph entry points
+    def index_shapes(self, B: int, H: int, W: int) -> List[Tuple[int, int, int, int]]:
+        """Shapes of the per-codebook index maps for a [B,3,H,W] input."""
+        div = {4: 2, 2: 4, 1: 8}[self.scale]
+        h, w = H // div, W // div
+        return [(B, 1, h * cs // 32, w * cs // 32) for cs, _n, _e in self.codebooks]
+
     def forward(self, x: torch.Tensor, want_indices: bool = True, want_loss: bool = True,
-                taps: Optional[List[str]] = None):
+                taps: Optional[List[str]] = None, gt_indices=None):
         """encode_and_decode.  x [B,3,H,W] fp32 cuda -> (y [B,3,sH,sW], loss scalar tensor | None,
-        indices [B,1,h,w] int64 | None[, {stage: NHWC tensor}])."""
+        indices [B,1,h,w] int64 | None[, {stage: NHWC tensor}]); multi-scale nets return a list of index maps, one
+        per codebook.  ``gt_indices`` (tensor or list, one map per codebook) selects the supervised loss of
+        femasr_arch.py:84-90 (LQ stage)."""
         if x.dim() != 4 or x.shape[1] != 3:
             raise L.FemasrError(f"expected input [B,3,H,W], got {tuple(x.shape)}")
         self._ensure(x.device)
@@ -136,7 +150,19 @@ class NativeNet:
             y = torch.empty((B, 3, H * s, W * s), dtype=torch.float32, device=self.device)
             div = {4: 2, 2: 4, 1: 8}[s]
             h, w = H // div, W // div
-            idx = torch.empty((B, 1, h, w), dtype=torch.int64, device=self.device) if want_indices else None
+            ishapes = self.index_shapes(B, H, W)
+            isizes = [math.prod(sh) for sh in ishapes]
+            flat = torch.empty(sum(isizes), dtype=torch.int64, device=self.device) if want_indices else None
+            idx = None
+            if want_indices:
+                parts = [p.view(sh) for p, sh in zip(torch.split(flat, isizes), ishapes)]
+                idx = parts[0] if len(parts) == 1 else parts
+            gt = None
+            if gt_indices is not None:
+                gl = [gt_indices] if torch.is_tensor(gt_indices) else list(gt_indices)
+                if len(gl) != len(ishapes) or any(g.numel() != n for g, n in zip(gl, isizes)):
+                    raise L.FemasrError(f"gt_indices must hold one map per codebook with {isizes} entries")
+                gt = torch.cat([g.detach().to(self.device, torch.int64).reshape(-1) for g in gl]).contiguous()
             loss = torch.empty((), dtype=torch.float32, device=self.device) if want_loss else None
             tap_out = {}
             if taps:
@@ -150,8 +176,8 @@ class NativeNet:
             L.check(self.lib.femasr_net_workspace_bytes(self._h, B, H, W, C.byref(need)))
             ws = self._workspace(need.value)
             try:
-                L.check(self.lib.femasr_net_forward(self._h, x.data_ptr(), y.data_ptr(), _ptr(idx), _ptr(loss),
-                                                    B, H, W, ws.data_ptr(), ws.numel(), _stream()))
+                L.check(self.lib.femasr_net_forward_gt(self._h, x.data_ptr(), y.data_ptr(), _ptr(flat), _ptr(loss),
+                                                       _ptr(gt), B, H, W, ws.data_ptr(), ws.numel(), _stream()))
             finally:
                 for name in tap_out:
                     self.lib.femasr_net_set_tap(self._h, name.encode(), None, 0)
@@ -194,7 +220,8 @@ class NativeNet:
         return {"in_conv": (B, H - 1, W - 1, c0), "down": (B, h, w, 256), "swin": (B, h, w, 256),
                 "up1": (B, 2 * h, 2 * w, 256), "up2": (B, 4 * h, 4 * w, 128), "z": (B, h, w, self.e_dim),
                 "zq": (B, h, w, self.e_dim), "after_quant": (B, h, w, 256), "dec0": (B, 2 * h, 2 * w, 256),
-                "dec1": (B, 4 * h, 4 * w, 128), "dec2": (B, 8 * h, 8 * w, 64)}
+                "dec1": (B, 4 * h, 4 * w, 128), "dec2": (B, 8 * h, 8 * w, 64),
+                **{f"z{k}": (B, h * cs // 32, w * cs // 32, e) for k, (cs, _n, e) in enumerate(self.codebooks) if k}}
 
     def decode_indices(self, indices: torch.Tensor) -> torch.Tensor:
         assert indices.dim() == 4, f"shape of indices must be (b, 1, h, w), but got {indices.shape}"

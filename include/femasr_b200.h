@@ -35,10 +35,12 @@ int femasr_device_cc(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Network-level API: replaces FeMaSRNet.encode_and_decode / test / decode_indices
- * (femasr_arch.py:311-374, 449-468, 376-385) for LQ_stage=True, norm 'gn', act 'silu',
- * one codebook at scale 32, scale_factor 2 or 4.
+ * (femasr_arch.py:311-374, 449-468, 376-385) for norm 'gn', act 'silu'; LQ_stage=True with scale_factor 2 or 4,
+ * or the HQ autoencoder (LQ_stage=False) as scale_factor 1; one codebook at scale 32, or the multi-scale
+ * variant (femasr_arch.py:280-299) with further codebooks at 64 / 128.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct femasr_net femasr_net;
+#define FEMASR_MAX_CODEBOOKS 3
 
 typedef struct {
   int scale_factor;   /* 2 or 4            (femasr_arch.py:225) */
@@ -48,6 +50,13 @@ typedef struct {
   int use_quantize;   /* femasr_arch.py:224,349-350: 0 => z_quant = feat_to_quant (VQ still runs) */
   int use_residual;   /* femasr_arch.py:226,361-362 */
   int gemm_path;      /* 0 = fp32 SIMT implicit GEMM, 1 = tcgen05 split-fp16 tensor-core GEMM */
+  /* multi-scale codebooks (femasr_arch.py:231-235, 280-299): rows of codebook_params.  n_codebooks 0 or 1 = the single
+   * codebook (32, n_e, e_dim) above; else cb_scale[0] must be 32 (it fixes the depth, :255-256), the others an
+   * increasing subset of {64, 128}; n_e / e_dim above are ignored. */
+  int n_codebooks;
+  int cb_scale[FEMASR_MAX_CODEBOOKS];
+  int cb_n_e[FEMASR_MAX_CODEBOOKS];     /* multiples of 64 */
+  int cb_e_dim[FEMASR_MAX_CODEBOOKS];   /* multiples of 64 */
 } femasr_net_config;
 
 int femasr_net_create(const femasr_net_config* cfg, femasr_net** out);
@@ -68,12 +77,21 @@ int femasr_net_workspace_bytes(femasr_net* net, int B, int H, int W, size_t* byt
  *   x_nchw    [B,3,H,W] fp32 device.  H,W such that the Swin stage (H/2 for x4, H/4 for x2) is a
  *             multiple of 8, else FEMASR_ERR_ARG (the reference raises from window_partition).
  *   y_nchw    [B,3,s*H,s*W] fp32 device, unclamped.
- *   indices   [B,1,h,w] int64 device (may be NULL).
- *   cb_loss   1 float device: codebook_loss = 1.25*mean((z_q-z)^2) (femasr_arch.py:84-92); may be NULL.
+ *   indices   [B,1,h,w] int64 device (may be NULL).  Multi-scale nets: the maps of all codebooks back to back in
+ *             codebook order ([B,1,h,w], then [B,1,2h,2w] for a codebook at 64, [B,1,4h,4w] at 128).
+ *   cb_loss   1 float device: codebook_loss = sum over codebooks of 1.25*mean((z_q-z)^2)
+ *             (femasr_arch.py:84-92, 371); may be NULL.
  */
 int femasr_net_forward(femasr_net* net, const float* x_nchw, float* y_nchw, int64_t* indices,
                        float* cb_loss, int B, int H, int W, void* workspace, size_t workspace_bytes,
                        void* stream);
+/* forward(input, gt_indices) (femasr_arch.py:470-474): gt_indices = the HQ stage's codes laid out like `indices`
+ * (all codebooks back to back).  They change only cb_loss, and only in the LQ stage (scale_factor 2 | 4):
+ * per codebook 0.25*mean((E[gt]-z)^2) + mean((G(z)-G(E[gt]))^2), G = per-image Gram matrix z^T z / hw
+ * (femasr_arch.py:40-48, 70-78, 87-90).  gt_indices == NULL is femasr_net_forward. */
+int femasr_net_forward_gt(femasr_net* net, const float* x_nchw, float* y_nchw, int64_t* indices,
+                          float* cb_loss, const int64_t* gt_indices, int B, int H, int W, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* decode_indices (femasr_arch.py:376-385): indices [B,1,h,w] int64 -> y [B,3,8h,8w]. */
 int femasr_net_decode_indices(femasr_net* net, const int64_t* indices, float* y_nchw, int B, int h,
@@ -82,7 +100,8 @@ int femasr_net_decode_workspace_bytes(femasr_net* net, int B, int h, int w, size
 
 /* Stage taps for parity tests: when `dst` is set for a stage name, the next forward copies that
  * stage's NHWC fp32 tensor there (device, `capacity` floats).  Names: in_conv, down, swin, up1, up2,
- * z, zq, after_quant, dec0, dec1, dec2.  dst == NULL removes the tap. */
+ * z, zq, after_quant, dec0, dec1, dec2 (z / zq / after_quant: first codebook), z1, z2 (features in front of the
+ * second / third codebook).  dst == NULL removes the tap. */
 int femasr_net_set_tap(femasr_net* net, const char* stage, float* dst, size_t capacity);
 /* Number of kernels the last femasr_net_forward launched (bench.py's gpu_launches). */
 int femasr_net_last_launch_count(femasr_net* net);
@@ -233,6 +252,19 @@ int femasr_vq_select(const float* z, const float* zc, const float* codebook, con
                      int write_zq_passthrough, void* stream);
 /* out[0] = scale * sum(x[0..n)) accumulated in double in a fixed order. */
 int femasr_sum_scaled(const float* x, float* out, size_t n, double scale, void* stream);
+/* out[0] += scale * sum(x[0..n)) (the running sum over codebooks, femasr_arch.py:371). */
+int femasr_sum_scaled_add(const float* x, float* out, size_t n, double scale, void* stream);
+/* torch.cat((a, nearest(b -> H x W)), dim=channels) on NHWC fp32: the before_quant input of the later codebooks
+ * (femasr_arch.py:332-335, Hb=H, Wb=W) and CombineQuantBlock (fema_utils.py:92-99, F.interpolate default mode). */
+int femasr_concat_channels(const float* a, int Ca, const float* b, int Hb, int Wb, int Cb, float* out, int B, int H,
+                           int W, void* stream);
+/* gt_indices loss branch (femasr_arch.py:70-78, 87-88): zq_gt[N,e] = codebook[gt], rows[i] = sum_k (zq_gt - z)^2. */
+int femasr_vq_gt_rows(const float* z, const float* codebook, const int64_t* gt, float* zq_gt, float* rows, int N,
+                      int n_e, int e_dim, void* stream);
+/* gram_loss (femasr_arch.py:40-48) on x, y [B,HW,C] (C multiple of 32): partial[B * femasr_gram_diff_tiles(C)] holds
+ * the per-tile sums of (x^T x / HW - y^T y / HW)^2; the loss is their sum / (B*C*C). */
+int femasr_gram_diff_tiles(int C);
+int femasr_gram_diff(const float* x, const float* y, float* partial, int B, int HW, int C, void* stream);
 /* get_codebook_entry (femasr_arch.py:102-112): zq[N,e] = codebook[idx]. */
 int femasr_codebook_gather(const int64_t* idx, const float* codebook, float* zq, int N, int n_e,
                            int e_dim, void* stream);

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for n in names:
         assert hasattr(dll, n), f"{n} declared in the header but not exported"
     assert sorted(lib.SIGNATURES) == names, "femasr_b200/lib.py SIGNATURES out of sync with the header"
-    assert lib.load().femasr_abi_version() == 1
+    assert lib.load().femasr_abi_version() == 2
 
 
 def test_argument_validation_without_gpu(built_lib):
@@ -52,6 +52,16 @@ def test_argument_validation_without_gpu(built_lib):
     assert abs(L.femasr_net_flops(h, 1, 128, 128) / 1e9 - 754.53) < 0.01
     assert L.femasr_net_params_complete(h) == -3
     L.femasr_net_destroy(h)
+    # multi-scale codebooks: geometry, workspace and the FLOP model follow the extra quantisers
+    I3 = ctypes.c_int * 3
+    cfg = lib.NetConfig(4, 0, 0, 3, 1, 1, 0, 2, I3(32, 64, 0), I3(1024, 512, 0), I3(256, 128, 0))
+    assert L.femasr_net_create(ctypes.byref(cfg), ctypes.byref(h)) == 0
+    assert L.femasr_net_workspace_bytes(h, 1, 32, 32, ctypes.byref(need)) == 0 and need.value > 0
+    extra = 2.0 * 512 * 128 + 2.0 * 512 * 128 + 2.0 * 9 * (128 + 256) * 256       # before_quant, z.E^T, after_quant at 128x128
+    assert abs(L.femasr_net_flops(h, 1, 128, 128) - (754.53e9 + extra * 128 * 128)) < 2e7
+    L.femasr_net_destroy(h)
+    cfg = lib.NetConfig(4, 0, 0, 3, 1, 1, 0, 2, I3(32, 32, 0), I3(1024, 512, 0), I3(256, 128, 0))
+    assert L.femasr_net_create(ctypes.byref(cfg), ctypes.byref(h)) == -1            # scales must increase
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -70,7 +80,16 @@ def test_unsupported_configs_raise():
     with pytest.raises(NotImplementedError):
         FeMaSRNet(codebook_params=[[32, 1024, 256]], LQ_stage=True, norm_type="bn")
     with pytest.raises(NotImplementedError):
-        FeMaSRNet(codebook_params=[[32, 1024, 256], [64, 512, 256]], LQ_stage=True)
+        FeMaSRNet(codebook_params=[[16, 1024, 256]], LQ_stage=True)               # first codebook must sit at 32
+    with pytest.raises(NotImplementedError):
+        FeMaSRNet(codebook_params=[[32, 1024, 256], [256, 512, 64]], LQ_stage=True)    # no decoder level at 256
+    with pytest.raises(NotImplementedError):
+        FeMaSRNet(codebook_params=[[32, 1000, 256]], LQ_stage=True)                # n_e / e_dim: multiples of 64
+    ms = FeMaSRNet(codebook_params=[[32, 1024, 256], [64, 512, 128]], LQ_stage=True)   # multi-scale codebooks
+    sd = ms.state_dict()
+    assert tuple(sd["before_quant_group.1.weight"].shape) == (128, 512, 1, 1)      # femasr_arch.py:292,297
+    assert tuple(sd["after_quant_group.1.conv.weight"].shape) == (256, 256 + 128, 3, 3)     # :293-294,298
+    assert tuple(sd["quantize_group.1.embedding.weight"].shape) == (512, 128)
     hq = FeMaSRNet(codebook_params=[[32, 1024, 256]], LQ_stage=False, scale_factor=4)    # HQ stage: scale forced to 1
     assert hq.scale_factor == 1 and not any("swin" in k for k in hq.state_dict())
 

@@ -4,9 +4,6 @@ and (b) the CPU oracle on fresh seeded inputs, stage by stage.
 
 Bars (BASELINE.json north_star): output max-abs <= 1e-3 fp32; codebook indices bit-exact.
 """
-import glob
-import os
-
 import numpy as np
 import pytest
 import torch
@@ -14,34 +11,41 @@ import torch
 from basicsr.archs.femasr_arch import FeMaSRNet
 from femasr_b200.spec import random_state_dict
 from oracle import femasr_oracle as O
+from tests.golden_util import GOLDEN, IDS, gt_indices_of, indices_of, load_case
 
 pytestmark = pytest.mark.gpu
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 OUT_ATOL = 1e-3
 
 
-def make_net(scale, e_dim, sd, cuda, **kw):
+def make_net(scale, e_dim, sd, cuda, codebooks=None, **kw):
     # scale 1 = the HQ autoencoder (LQ_stage=False).  gemm_path 0: the fp32-FFMA path (ATen-level rounding, tight tolerances below); the default tensor-core
     # path is exercised against the same goldens in tests/test_tc_gpu.py.
     kw.setdefault("gemm_path", 0)
-    net = FeMaSRNet(codebook_params=[[32, 1024, e_dim]], LQ_stage=scale != 1, scale_factor=scale, **kw)
+    net = FeMaSRNet(codebook_params=codebooks or [[32, 1024, e_dim]], LQ_stage=scale != 1, scale_factor=scale, **kw)
     net.load_state_dict(sd, strict=True)
     return net.to(cuda).eval()
 
 
-@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def check_indices(idx, g):
+    want = indices_of(g)
+    assert len(idx) == len(want)
+    for k, (a, b) in enumerate(zip(idx, want)):
+        assert a.dtype == torch.int64 and tuple(a.shape) == b.shape
+        mism = int((a.cpu().numpy() != b).sum())
+        assert mism == 0, f"codebook {k}: {mism}/{b.size} index mismatches"
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=IDS)
 def test_golden_through_public_surface(cuda, path):
-    g = np.load(path)
+    g, sd, cbs = load_case(path)
     scale, e_dim, entry = int(g["scale"]), int(g["e_dim"]), str(g["entry"])
-    sd = random_state_dict(scale, e_dim, seed=int(g["seed"]), init=str(g["init"]))
-    net = make_net(scale, e_dim, sd, cuda)
+    net = make_net(scale, e_dim, sd, cuda, codebooks=cbs)
     x = torch.from_numpy(g["input"]).to(cuda)
     with torch.no_grad():
         if entry == "forward":
-            out, loss, sem, idx = net(x)
-            assert idx[0].dtype == torch.int64 and tuple(idx[0].shape) == g["indices"].shape
-            mism = int((idx[0].cpu().numpy() != g["indices"]).sum())
-            assert mism == 0, f"{mism}/{g['indices'].size} codebook index mismatches"
+            gt = gt_indices_of(g)
+            out, loss, sem, idx = net(x, gt) if gt is not None else net(x)
+            check_indices(idx, g)
             np.testing.assert_allclose(loss.item(), float(g["loss"]), rtol=2e-5)
             assert sem.item() == 0.0
         elif entry == "test":

@@ -228,3 +228,87 @@ def test_bad_arguments_raise(cuda):
     assert lib.femasr_ln_stats(out.data_ptr(), out.data_ptr(), out.data_ptr(), 4, 128, 1e-5, G.S()) == -1
     with pytest.raises(L.FemasrError):
         L.check(lib.femasr_flip_pad(out.data_ptr(), out.data_ptr(), 1, 1, 4, 4, 9, 4, G.S()))
+
+
+@pytest.mark.parametrize("B,H,W,Ca,Hb,Wb,Cb", [(2, 8, 12, 256, 8, 12, 256), (1, 16, 8, 128, 8, 4, 256),
+                                              (2, 16, 16, 64, 4, 4, 128), (1, 6, 9, 64, 3, 3, 64)])
+def test_concat_channels_nearest(cuda, B, H, W, Ca, Hb, Wb, Cb):
+    """torch.cat((a, F.interpolate(b, a.shape[2:])), 1): femasr_arch.py:332-335 (same size) and fema_utils.py:92-99."""
+    a, b = rnd(B, Ca, H, W, seed=60), rnd(B, Cb, Hb, Wb, seed=61)
+    want = torch.cat((a, F.interpolate(b, (H, W))), dim=1)
+    out = torch.empty(B, H, W, Ca + Cb, device=cuda)
+    ag, bg = G.nhwc(a).to(cuda), G.nhwc(b).to(cuda)
+    L.check(L.load().femasr_concat_channels(G.p(ag), Ca, G.p(bg), Hb, Wb, Cb, G.p(out), B, H, W, G.S()))
+    assert torch.equal(G.nchw(out).cpu(), want)
+
+
+@pytest.mark.parametrize("B,h,w,e,n_e", [(2, 16, 16, 256, 1024), (1, 8, 12, 128, 512), (3, 5, 7, 64, 256)])
+def test_gt_indices_loss_terms(cuda, B, h, w, e, n_e):
+    """The supervised VQ loss (femasr_arch.py:70-78, 84-90) assembled from vq_gt_rows + gram_diff + sum_scaled(_add)."""
+    lib = L.load()
+    z = rnd(B, e, h, w, seed=62)
+    cb = rnd(n_e, e, seed=63, scale=0.7)
+    gt = torch.randint(0, n_e, (B, 1, h, w), generator=torch.Generator().manual_seed(64))
+    _, want, _ = O.vector_quantize(cb, z, gt, lq=True)
+    N = B * h * w
+    zg, cbg, gtg = G.nhwc(z).to(cuda), cb.to(cuda), gt.to(cuda)
+    zq_gt, rows = torch.empty(N, e, device=cuda), torch.empty(N, device=cuda)
+    L.check(lib.femasr_vq_gt_rows(G.p(zg), G.p(cbg), G.p(gtg), G.p(zq_gt), G.p(rows), N, n_e, e, G.S()))
+    assert torch.equal(zq_gt.cpu(), cb[gt.reshape(-1)])
+    tiles = lib.femasr_gram_diff_tiles(e)
+    assert tiles == (e // 32) ** 2
+    part = torch.empty(B * tiles, device=cuda)
+    L.check(lib.femasr_gram_diff(G.p(zg), G.p(zq_gt), G.p(part), B, h * w, e, G.S()))
+    zf = z.permute(0, 2, 3, 1).reshape(B, h * w, e).double()
+    yf = cb[gt.reshape(-1)].reshape(B, h * w, e).double()
+    gram = ((zf.transpose(1, 2) @ zf - yf.transpose(1, 2) @ yf) / (h * w)).square().sum()
+    assert abs(part.double().sum().item() - gram.item()) <= 2e-5 * gram.item()
+    loss = torch.full((1,), 123.0, device=cuda)
+    L.check(lib.femasr_sum_scaled(G.p(rows), G.p(loss), N, 0.25 / (N * e), G.S()))
+    L.check(lib.femasr_sum_scaled_add(G.p(part), G.p(loss), B * tiles, 1.0 / (B * e * e), G.S()))
+    assert abs(loss.item() - want.item()) <= 2e-5 * abs(want.item())
+
+
+@pytest.mark.parametrize("scale,cbs,shape,path", [
+    (4, [[32, 1024, 256], [64, 512, 128]], (2, 3, 48, 32), 0),
+    (4, [[32, 1024, 256], [64, 512, 128]], (2, 3, 48, 32), 1),
+    (2, [[32, 512, 256], [64, 512, 256], [128, 256, 128]], (1, 3, 64, 96), 1),
+    (1, [[32, 1024, 256], [128, 256, 64]], (1, 3, 64, 128), 1),
+    (4, [[32, 1024, 256], [128, 512, 64]], (1, 3, 32, 48), 1)])
+def test_multiscale_codebooks_against_oracle(cuda, scale, cbs, shape, path):
+    """Multi-scale codebooks (femasr_arch.py:280-299, 329-359) on fresh seeded inputs, both GEMM paths: every codebook's
+    indices bit-exact, features in front of the later quantisers and the output within the fp32 bars."""
+    from basicsr.archs.femasr_arch import FeMaSRNet
+    from femasr_b200.spec import random_state_dict
+    sd = random_state_dict(scale, cbs[0][2], seed=70, init="perturbed", codebooks=cbs)
+    net = FeMaSRNet(codebook_params=cbs, LQ_stage=scale != 1, scale_factor=scale, gemm_path=path)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda).eval()
+    x = torch.rand(shape, generator=torch.Generator().manual_seed(71))
+    gt = None
+    if scale != 1:
+        div = {4: 2, 2: 4}[scale]
+        gt = [torch.randint(0, n, (shape[0], 1, shape[2] // div * s // 32, shape[3] // div * s // 32),
+                            generator=torch.Generator().manual_seed(72 + k)) for k, (s, n, _e) in enumerate(cbs)]
+    with torch.no_grad():
+        want, wloss, _, widx = O.encode_and_decode(sd, x, scale, cb_scales=[c[0] for c in cbs])
+        out, loss, sem, idx = net(x.to(cuda))
+        eng = net._native(torch.device(cuda))
+        names = [f"z{k}" for k in range(1, len(cbs))]
+        taps = eng.forward(x.to(cuda), taps=names)[3]
+    assert len(idx) == len(cbs)
+    for k, (a, b) in enumerate(zip(idx, widx)):
+        assert tuple(a.shape) == tuple(b.shape)
+        mism = int((a.cpu() != b).sum())
+        assert mism == 0, f"codebook {k}: {mism}/{b.numel()} index mismatches"
+    assert abs(loss.item() - wloss.item()) <= (1e-4 if path else 2e-5) * abs(wloss.item())
+    err = (out.cpu() - want).abs().max().item()
+    print(f"multi-scale x{scale} {cbs} path {path}: output max-abs {err:.2e}")
+    assert err <= 1e-3
+    assert all(t.isfinite().all() for t in taps.values())
+    if gt is not None:
+        with torch.no_grad():
+            _, wl2, _, _ = O.encode_and_decode(sd, x, scale, cb_scales=[c[0] for c in cbs], gt_indices=gt)
+            out2, l2, _, idx2 = net(x.to(cuda), gt)
+        assert torch.equal(out2, out) and all(torch.equal(a, b) for a, b in zip(idx, idx2)), "gt_indices only change the loss"
+        assert abs(l2.item() - wl2.item()) <= 1e-4 * abs(wl2.item())

@@ -256,25 +256,29 @@ def test_tc_prologues(cuda):
     assert (got - want).abs().max().item() <= 5e-6
 
 
-def make_net(scale, e_dim, sd, cuda):
+def make_net(scale, e_dim, sd, cuda, codebooks=None):
     from basicsr.archs.femasr_arch import FeMaSRNet
-    net = FeMaSRNet(codebook_params=[[32, 1024, e_dim]], LQ_stage=scale != 1, scale_factor=scale, gemm_path=1)
+    net = FeMaSRNet(codebook_params=codebooks or [[32, 1024, e_dim]], LQ_stage=scale != 1, scale_factor=scale, gemm_path=1)
     net.load_state_dict(sd, strict=True)
     return net.to(cuda).eval()
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_golden_tensor_core_path(cuda, path):
-    g = np.load(path)
+    from tests.golden_util import gt_indices_of, indices_of, load_case
+    g, sd, cbs = load_case(path)
     scale, e_dim, entry = int(g["scale"]), int(g["e_dim"]), str(g["entry"])
-    sd = random_state_dict(scale, e_dim, seed=int(g["seed"]), init=str(g["init"]))
-    net = make_net(scale, e_dim, sd, cuda)
+    net = make_net(scale, e_dim, sd, cuda, codebooks=cbs)
     x = torch.from_numpy(g["input"]).to(cuda)
     with torch.no_grad():
         if entry == "forward":
-            out, loss, sem, idx = net(x)
-            mism = int((idx[0].cpu().numpy() != g["indices"]).sum())
-            assert mism == 0, f"{mism}/{g['indices'].size} codebook index mismatches"
+            gt = gt_indices_of(g)
+            out, loss, sem, idx = net(x, gt) if gt is not None else net(x)
+            want = indices_of(g)
+            assert len(idx) == len(want)
+            for k, (a, b) in enumerate(zip(idx, want)):
+                mism = int((a.cpu().numpy() != b).sum())
+                assert mism == 0, f"codebook {k}: {mism}/{b.size} index mismatches"
             # the tensor-core accumulator truncates (round-toward-zero) once per MMA, which shrinks |z| by ~1e-5
             # systematically; the loss (~mean z^2) moves by twice that.  Indices stay bit-exact.
             np.testing.assert_allclose(loss.item(), float(g["loss"]), rtol=1e-4)
