@@ -95,6 +95,7 @@ struct femasr_net {
   std::map<std::string, ParamInfo> spec;
   std::map<std::string, DevBuf> raw;      // fp32 copy in the reference layout
   std::map<std::string, DevBuf> packed;   // K-major GEMM operand / expanded rel bias / codebook^T
+  std::map<std::string, DevBuf> packed_mma;   // rel-pos bias in the mma attention kernel's fragment order
   std::map<std::string, DevBuf> tcw;      // tensor-core operand (split fp16), gemm_path 1
   std::map<std::string, DevBuf> tcw_up;   // sub-pixel phase filters of the upsample-fused 3x3 convs
   std::map<std::string, DevBuf> esq;      // sum e^2 per codebook row, keyed by the codebook's parameter name
@@ -113,6 +114,7 @@ struct femasr_net {
     for (auto& r : prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto& kv : raw) cudaFree(kv.second.p);
     for (auto& kv : packed) cudaFree(kv.second.p);
+    for (auto& kv : packed_mma) cudaFree(kv.second.p);
     for (auto& kv : tcw) cudaFree(kv.second.p);
     for (auto& kv : tcw_up) cudaFree(kv.second.p);
     for (auto& kv : esq) cudaFree(kv.second.p);
@@ -428,8 +430,9 @@ struct Ctx {
           __half* hd_hi = reinterpret_cast<__half*>(hid); __half* hd_lo = hd_hi + M * 4 * C;
           conv_tc(bp + ".attn.qkv", in, qkv, B, H, W, C, 3 * C, 1, 0, FEMASR_PRO_LN, nullptr, nullptr, P(bp + ".norm1.weight"),
                   P(bp + ".norm1.bias"), 0, nullptr, nullptr);
+          const float* rbm = dry() ? nullptr : net->packed_mma[bp + ".attn.relative_position_bias_table"].p;
           run("window_attention_mma", attn_flops, [&] {
-            return femasr_window_attention_mma(qkv, rb, nullptr, ao_hi, ao_lo, B, H, W, C, 8, (b & 1) ? 4 : 0, st);
+            return femasr_window_attention_mma(qkv, rbm, nullptr, ao_hi, ao_lo, B, H, W, C, 8, (b & 1) ? 4 : 0, st);
           });
           conv_tc(bp + ".attn.proj", nullptr, T, B, H, W, C, C, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0,
                   in, nullptr, ao_hi, ao_lo);
@@ -772,6 +775,10 @@ extern "C" int femasr_net_set_param(femasr_net* net, const char* name, const flo
   if (pi.kind == 2) {
     DevBuf& pb = net->packed[key];
     if (!pb.p) { FEMASR_CUDA(cudaMalloc(&pb.p, 8 * 64 * 64 * sizeof(float))); pb.n = 8 * 64 * 64; }
+    DevBuf& mb = net->packed_mma[key];
+    if (!mb.p) { FEMASR_CUDA(cudaMalloc(&mb.p, 8 * 64 * 64 * sizeof(float))); mb.n = 8 * 64 * 64; }
+    int s = femasr_expand_rel_bias_mma(rb.p, mb.p, 8, st);
+    if (s) return s;
     return femasr_expand_rel_bias(rb.p, pb.p, 8, st);
   }
   if (pi.kind == 3) {

@@ -90,6 +90,7 @@ SIGNATURES = {
     "femasr_window_attention": (_I, [_V, _V, _V, _I, _I, _I, _I, _I, _I, _V]),
     "femasr_window_attention_mma": (_I, [_V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _I, _V]),
     "femasr_expand_rel_bias": (_I, [_V, _V, _I, _V]),
+    "femasr_expand_rel_bias_mma": (_I, [_V, _V, _I, _V]),
     "femasr_row_sumsq": (_I, [_V, _V, _I, _I, _V]),
     "femasr_vq_select": (_I, [_V, _V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _V]),
     "femasr_sum_scaled": (_I, [_V, _V, _Z, _D, _V]),

@@ -237,11 +237,14 @@ int femasr_ln_stats(const float* x, float* mean, float* rstd, int M, int C, floa
  * bias_full [heads][64][64] = relative_position_bias_table[relative_position_index] (:127-129). */
 int femasr_window_attention(const float* qkv, const float* bias_full, float* out, int B, int H, int W,
                             int C, int heads, int shift, void* stream);
-/* Same contract on warp-level tensor cores (mma.sync m16n8k16, 3-term split-fp16, fp32 softmax). */
-int femasr_window_attention_mma(const float* qkv, const float* bias_full, float* out, void* out_hi, void* out_lo,
+/* Same contract on warp-level tensor cores (mma.sync m16n8k16, 3-term split-fp16, fp32 softmax); heads*32 == C.
+ * bias_frag: the same [heads][64][64] bias values in the kernel's accumulator-fragment order, made by
+ * femasr_expand_rel_bias_mma (one coalesced 16-byte load per lane and n-tile instead of 16 strided 8-byte ones).
+ * out_hi/out_lo non-NULL: the result is written as split fp16 planes [B*H*W, C] instead of fp32 `out`. */
+int femasr_window_attention_mma(const float* qkv, const float* bias_frag, float* out, void* out_hi, void* out_lo,
                                 int B, int H, int W, int C, int heads, int shift, void* stream);
-/* (out_hi/out_lo non-NULL: the result is written as split fp16 planes [B*H*W, C] instead of fp32 `out`) */
 int femasr_expand_rel_bias(const float* table /*[225,heads]*/, float* bias_full, int heads, void* stream);
+int femasr_expand_rel_bias_mma(const float* table /*[225,heads]*/, float* bias_frag /*heads*4096*/, int heads, void* stream);
 
 /* VectorQuantizer.forward (femasr_arch.py:50-100) given zc = z @ codebook^T:
  *   d_j = fl(fl(sum z^2 + esq_j) - 2*zc_j), idx = argmin (lowest index on ties), zq = z + (e_idx - z),

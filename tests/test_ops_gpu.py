@@ -116,11 +116,18 @@ def test_window_attention(cuda, H, W, shift):
     L.check(lib.femasr_window_attention(qkvg.data_ptr(), full.data_ptr(), out.data_ptr(), B, H, W, Cc, 8, shift, G.S()))
     close(out, want, 2e-5, "window attention")
     out2 = torch.zeros(B, H * W, Cc, device=cuda)
-    L.check(lib.femasr_window_attention_mma(qkvg.data_ptr(), full.data_ptr(), out2.data_ptr(), None, None, B, H, W, Cc, 8, shift, G.S()))
+    frag = torch.empty(8 * 64 * 64, device=cuda)         # the same bias in the mma kernel's accumulator-fragment order
+    L.check(lib.femasr_expand_rel_bias_mma(tb.data_ptr(), frag.data_ptr(), 8, G.S()))
+    fr = frag.view(8, 4, 8, 8, 4, 2, 2).cpu()            # [h][warp][nt][g][c][row half][col]
+    rows = (16 * torch.arange(4)[:, None, None] + torch.arange(8)[None, :, None] + 8 * torch.arange(2)[None, None, :])   # [warp][g][rh]
+    cols = (8 * torch.arange(8)[:, None, None] + 2 * torch.arange(4)[None, :, None] + torch.arange(2)[None, None, :])    # [nt][c][e]
+    want_fr = bias[:, rows[:, None, :, None, :, None], cols[None, :, None, :, None, :]]
+    assert torch.equal(fr, want_fr), "fragment-order bias expansion"
+    L.check(lib.femasr_window_attention_mma(qkvg.data_ptr(), frag.data_ptr(), out2.data_ptr(), None, None, B, H, W, Cc, 8, shift, G.S()))
     close(out2, want, 2e-5, "window attention (mma.sync split-fp16)")
     oh = torch.zeros(B, H * W, Cc, dtype=torch.float16, device=cuda)
     ol = torch.zeros_like(oh)
-    L.check(lib.femasr_window_attention_mma(qkvg.data_ptr(), full.data_ptr(), None, oh.data_ptr(), ol.data_ptr(), B, H, W, Cc, 8, shift, G.S()))
+    L.check(lib.femasr_window_attention_mma(qkvg.data_ptr(), frag.data_ptr(), None, oh.data_ptr(), ol.data_ptr(), B, H, W, Cc, 8, shift, G.S()))
     close(oh.float() + ol.float(), want, 2e-5, "window attention (split fp16 planes out)")
 
 
