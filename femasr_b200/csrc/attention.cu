@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(128) window_attention_mma_kernel(const float* 
                                                                    __half* __restrict__ out_lo, int H, int W, int C,
                                                                    int heads, int shift) {
   __shared__ __align__(16) __half Kh[WT * KV_LD], Kl[WT * KV_LD];   // [key][k-index]  (k-index = permuted head dim)
-  __shared__ __align__(16) __half Vh[WT * KV_LD], Vl[WT * KV_LD];   // [key][dim]
+  __shared__ __align__(16) __half Vh[WT * KV_LD], Vl[WT * KV_LD];   // [key][permuted dim]
   __shared__ __align__(8) int region[WT];
   __shared__ long toks[WT];
   const int head = blockIdx.x % heads;
@@ -164,8 +164,10 @@ __global__ void __launch_bounds__(128) window_attention_mma_kernel(const float* 
       *reinterpret_cast<uint32_t*>(&Kl[j * KV_LD + posA]) = l0; *reinterpret_cast<uint32_t*>(&Kl[j * KV_LD + posB]) = l1;
       split2(vv.x, vv.y, h0, l0);
       split2(vv.z, vv.w, h1, l1);
-      *reinterpret_cast<uint2*>(&Vh[j * KV_LD + 4 * q]) = make_uint2(h0, h1);
-      *reinterpret_cast<uint2*>(&Vl[j * KV_LD + 4 * q]) = make_uint2(l0, l1);
+      // V columns get the same permutation: n-tile nt, column 2c+e of the P.V accumulator is then physical dim
+      // 8c+2nt+e, i.e. a lane ends up with 8 CONTIGUOUS output dims (one 16-byte store per plane and row)
+      *reinterpret_cast<uint32_t*>(&Vh[j * KV_LD + posA]) = h0; *reinterpret_cast<uint32_t*>(&Vh[j * KV_LD + posB]) = h1;
+      *reinterpret_cast<uint32_t*>(&Vl[j * KV_LD + posA]) = l0; *reinterpret_cast<uint32_t*>(&Vl[j * KV_LD + posB]) = l1;
     }
   }
   // this warp's bias fragments (independent of the window): issue the loads before the barrier
@@ -270,20 +272,24 @@ __global__ void __launch_bounds__(128) window_attention_mma_kernel(const float* 
     }
   }
   const float i0 = 1.0f / sum0, i1 = 1.0f / sum1;
-  const long e0 = toks[r0] * C + head * HD, e1 = toks[r1] * C + head * HD;
+  // lane c of a quad holds dims [8c, 8c+8) of rows r0 / r1 (see the V permutation above)
+  const long e0 = toks[r0] * C + head * HD + 8 * c, e1 = toks[r1] * C + head * HD + 8 * c;
+  if (out_hi) {              // split fp16 planes: directly the proj GEMM's A operand
+    uint32_t h0[4], l0[4], h1[4], l1[4];
 #pragma unroll
-  for (int nt = 0; nt < 4; ++nt) {
-    const int col = 8 * nt + 2 * c;
-    if (out_hi) {            // split fp16 planes: directly the proj GEMM's A operand
-      uint32_t h, l;
-      split2(o[nt][0] * i0, o[nt][1] * i0, h, l);
-      *reinterpret_cast<uint32_t*>(out_hi + e0 + col) = h; *reinterpret_cast<uint32_t*>(out_lo + e0 + col) = l;
-      split2(o[nt][2] * i1, o[nt][3] * i1, h, l);
-      *reinterpret_cast<uint32_t*>(out_hi + e1 + col) = h; *reinterpret_cast<uint32_t*>(out_lo + e1 + col) = l;
-    } else {
-      *reinterpret_cast<float2*>(out + e0 + col) = make_float2(o[nt][0] * i0, o[nt][1] * i0);
-      *reinterpret_cast<float2*>(out + e1 + col) = make_float2(o[nt][2] * i1, o[nt][3] * i1);
+    for (int nt = 0; nt < 4; ++nt) {
+      split2(o[nt][0] * i0, o[nt][1] * i0, h0[nt], l0[nt]);
+      split2(o[nt][2] * i1, o[nt][3] * i1, h1[nt], l1[nt]);
     }
+    *reinterpret_cast<uint4*>(out_hi + e0) = make_uint4(h0[0], h0[1], h0[2], h0[3]);
+    *reinterpret_cast<uint4*>(out_lo + e0) = make_uint4(l0[0], l0[1], l0[2], l0[3]);
+    *reinterpret_cast<uint4*>(out_hi + e1) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+    *reinterpret_cast<uint4*>(out_lo + e1) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+  } else {
+    *reinterpret_cast<float4*>(out + e0) = make_float4(o[0][0] * i0, o[0][1] * i0, o[1][0] * i0, o[1][1] * i0);
+    *reinterpret_cast<float4*>(out + e0 + 4) = make_float4(o[2][0] * i0, o[2][1] * i0, o[3][0] * i0, o[3][1] * i0);
+    *reinterpret_cast<float4*>(out + e1) = make_float4(o[0][2] * i1, o[0][3] * i1, o[1][2] * i1, o[1][3] * i1);
+    *reinterpret_cast<float4*>(out + e1 + 4) = make_float4(o[2][2] * i1, o[2][3] * i1, o[3][2] * i1, o[3][3] * i1);
   }
 }
 

@@ -261,6 +261,158 @@ extern "C" int femasr_out_conv3x3(const float* x, const float* w, const float* b
   return launch_status("out_conv_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------
+// out_conv on warp-level tensor cores (mma.sync m16n8k16, 3-term split fp16 like the big GEMMs), used by the
+// tensor-core path.  The SIMT kernel above is bound by shared-memory reads (576 values per pixel for 3 outputs).
+// Here the three horizontal taps are folded into the N dimension: for an output row y the warp accumulates
+//     Q[x'][kw*3+co] = sum_kh sum_c X[y+kh-1][x'][c] * W[kh][kw][c][co]        (M = pixels x', N = 9 -> 16, K = 3*64)
+// for the 32 halo pixels x' of its row (two m-tiles), so every activation fragment is fetched ONCE per (kh, 16
+// channels) instead of once per tap, and then   out[x][co] = bias + Q[x][co] + Q[x+1][3+co] + Q[x+2][6+co]
+// (a 3-term shift-add through a per-warp scratch).  Tile: 8 output rows x 30 columns per CTA (warp = row).
+constexpr int OM_TH = 8, OM_TW = 30, OM_PX = 32, OM_PB = 144;     // halo pixels per row, bytes per pixel and plane (128 + pad)
+constexpr int OM_PLANE = (OM_TH + 2) * OM_PX * OM_PB;             // 46080 B per fp16 plane
+constexpr int OM_SMEM = 2 * OM_PLANE + OM_TH * OM_PX * 9 * (int)sizeof(float);
+constexpr float OM_WSCALE = 256.0f;                               // weights * 2^8: keeps the lo plane out of fp16 subnormals
+__device__ uint32_t g_outconv_bfrag[3 * 4 * 2 * 2 * 2 * 32];       // [kh][kc][nt][plane][reg][lane] B fragments (refreshed per call)
+
+// (x, y) -> packed fp16 pairs hi = rn(v), lo = rn(v - hi), saturating at +-65504 like the big GEMMs' operand staging
+__device__ __forceinline__ void oc_split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y), "f"(x));
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(y - hf.y), "f"(x - hf.x));
+}
+
+// w: K-major packed [tap][c][co] fp32 (femasr_pack_weight).  One thread per (kh, kc, nt, reg, lane).
+__global__ void out_conv_bfrag_kernel(const float* __restrict__ w) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 3 * 4 * 2 * 2 * 32) return;
+  const int lane = idx & 31, reg = (idx >> 5) & 1, nt = (idx >> 6) & 1, kc = (idx >> 7) & 3, kh = idx >> 9;
+  const int g = lane >> 2, cq = lane & 3;
+  const int n = nt * 8 + g;                       // column = kw*3 + co
+  float v0 = 0.f, v1 = 0.f;
+  if (n < 9) {
+    const int kw = n / 3, co = n - 3 * kw;
+    const int ch = 16 * kc + 2 * cq + 8 * reg;    // B fragment: b0 = k 2c,2c+1; b1 = k 2c+8,2c+9
+    v0 = w[(((kh * 3 + kw) * OC_CIN) + ch) * 3 + co] * OM_WSCALE;
+    v1 = w[(((kh * 3 + kw) * OC_CIN) + ch + 1) * 3 + co] * OM_WSCALE;
+  }
+  uint32_t hi, lo;
+  oc_split2(v0, v1, hi, lo);
+  const int base = (((kh * 4 + kc) * 2 + nt) * 2) * 2;        // [plane][reg]
+  g_outconv_bfrag[(base + 0 * 2 + reg) * 32 + lane] = hi;
+  g_outconv_bfrag[(base + 1 * 2 + reg) * 32 + lane] = lo;
+}
+
+__global__ void __launch_bounds__(OM_TH * 32, 2) out_conv_mma_kernel(const float* __restrict__ x, const float* __restrict__ bias,
+                                                                     float* __restrict__ y, int B, int H, int W) {
+  extern __shared__ __align__(16) uint8_t om_smem[];
+  uint8_t* plane_hi = om_smem;
+  uint8_t* plane_lo = om_smem + OM_PLANE;
+  float* qs_all = reinterpret_cast<float*>(om_smem + 2 * OM_PLANE);
+  const int x0 = blockIdx.x * OM_TW - 1, y0 = blockIdx.y * OM_TH - 1, b = blockIdx.z;     // halo origin
+  // stage the (TH+2) x 32 halo pixels as split fp16: 16 consecutive threads fetch one pixel's 256 bytes
+  for (int i = threadIdx.x; i < (OM_TH + 2) * OM_PX * (OC_CIN / 4); i += OM_TH * 32) {
+    const int c4 = i & 15, pp = i >> 4;
+    const int px = pp & (OM_PX - 1), py = pp >> 5;
+    const int gy = y0 + py, gx = x0 + px;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+      v = __ldg(reinterpret_cast<const float4*>(x + (((long)b * H + gy) * W + gx) * OC_CIN) + c4);
+    uint32_t h0, l0, h1, l1;
+    oc_split2(v.x, v.y, h0, l0);
+    oc_split2(v.z, v.w, h1, l1);
+    const int off = pp * OM_PB + c4 * 8;
+    *reinterpret_cast<uint2*>(plane_hi + off) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(plane_lo + off) = make_uint2(l0, l1);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, cq = lane & 3;
+  float acc[2][2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+  // ldmatrix row address: lane -> pixel (lane & 7) + 8 * ((lane >> 3) & 1) of the m-tile, channel block 8 * (lane >> 4)
+  const int lpx = (lane & 7) + 8 * ((lane >> 3) & 1), lch = 8 * (lane >> 4);
+  const uint32_t hi_base = (uint32_t)__cvta_generic_to_shared(plane_hi), lo_base = (uint32_t)__cvta_generic_to_shared(plane_lo);
+#pragma unroll 1
+  for (int kh = 0; kh < 3; ++kh) {
+    uint32_t bh[4][2][2], bl[4][2][2];            // [kc][nt][reg]
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int base = (((kh * 4 + kc) * 2 + nt) * 2) * 2;
+          bh[kc][nt][r] = g_outconv_bfrag[(base + r) * 32 + lane];
+          bl[kc][nt][r] = g_outconv_bfrag[(base + 2 + r) * 32 + lane];
+        }
+    const int row = warp + kh;                    // halo row feeding output row `warp` through tap row kh
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint32_t off = (uint32_t)((row * OM_PX + mt * 16 + lpx) * OM_PB + (kc * 16 + lch) * 2);
+        uint32_t ah[4], al[4];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(ah[0]), "=r"(ah[1]), "=r"(ah[2]), "=r"(ah[3]) : "r"(hi_base + off));
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(al[0]), "=r"(al[1]), "=r"(al[2]), "=r"(al[3]) : "r"(lo_base + off));
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          float(&d)[4] = acc[mt][nt];
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                       : "r"(al[0]), "r"(al[1]), "r"(al[2]), "r"(al[3]), "r"(bh[kc][nt][0]), "r"(bh[kc][nt][1]));
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                       : "r"(ah[0]), "r"(ah[1]), "r"(ah[2]), "r"(ah[3]), "r"(bl[kc][nt][0]), "r"(bl[kc][nt][1]));
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                       : "r"(ah[0]), "r"(ah[1]), "r"(ah[2]), "r"(ah[3]), "r"(bh[kc][nt][0]), "r"(bh[kc][nt][1]));
+        }
+      }
+  }
+  // shift-add over the three horizontal taps through this warp's scratch Q[32 pixels][9]
+  float* qs = qs_all + warp * OM_PX * 9;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int p0 = mt * 16 + g, p1 = p0 + 8;
+    qs[p0 * 9 + 2 * cq] = acc[mt][0][0]; qs[p0 * 9 + 2 * cq + 1] = acc[mt][0][1];
+    qs[p1 * 9 + 2 * cq] = acc[mt][0][2]; qs[p1 * 9 + 2 * cq + 1] = acc[mt][0][3];
+    if (cq == 0) { qs[p0 * 9 + 8] = acc[mt][1][0]; qs[p1 * 9 + 8] = acc[mt][1][2]; }
+  }
+  __syncwarp();
+  const int oy = blockIdx.y * OM_TH + warp, ox = blockIdx.x * OM_TW + lane;
+  if (lane < OM_TW && oy < H && ox < W) {
+    const long plane = (long)H * W;
+    float* o = y + (long)b * 3 * plane + (long)oy * W + ox;
+    const float inv = 1.0f / OM_WSCALE;
+#pragma unroll
+    for (int co = 0; co < 3; ++co)
+      o[co * plane] = __ldg(bias + co) + ((qs[lane * 9 + co] + qs[(lane + 1) * 9 + 3 + co]) + qs[(lane + 2) * 9 + 6 + co]) * inv;
+  }
+}
+
+extern "C" int femasr_out_conv3x3_mma(const float* x, const float* w, const float* bias, float* y, int B, int H, int W,
+                                      int Cin, void* stream) {
+  FEMASR_CHECK_ARG(x && w && bias && y, "out_conv_mma: null pointer");
+  FEMASR_CHECK_ARG(B > 0 && H > 0 && W > 0, "out_conv_mma: empty input");
+  FEMASR_CHECK_ARG(Cin == OC_CIN, "out_conv_mma: Cin must be 64 (channel_query_dict[256])");
+  FEMASR_CHECK_ARG(cdiv(H, OM_TH) <= 65535 && B <= 65535, "out_conv_mma: grid too large");
+  cudaStream_t st = as_stream(stream);
+  out_conv_bfrag_kernel<<<6, 256, 0, st>>>(w);     // stream-ordered refresh of the B fragments (several engines can coexist)
+  static bool attr_set = false;
+  if (!attr_set) {
+    FEMASR_CUDA(cudaFuncSetAttribute(out_conv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OM_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)cdiv(W, OM_TW), (unsigned)cdiv(H, OM_TH), B);
+  out_conv_mma_kernel<<<grid, OM_TH * 32, OM_SMEM, st>>>(x, bias, y, B, H, W);
+  return launch_status("out_conv_mma_kernel");
+}
+
 extern "C" int femasr_pack_weight(const float* w, float* out, int Cout, int Cin, int kh, int kw, void* stream) {
   FEMASR_CHECK_ARG(w && out && Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "pack_weight: bad argument");
   const long n = (long)Cout * Cin * kh * kw;

@@ -107,6 +107,7 @@ struct femasr_net {
   int last_launches = 0;
   bool profile = false;
   bool tc_precise = true;                 // K-sliced fp32 accumulation for the layers in front of the VQ
+  bool oc_mma = true;                     // out_conv on mma.sync in the tensor-core path (FEMASR_OUTCONV_MMA=0: SIMT kernel)
   bool fast_silu = true;                  // approximate-unit SiLU in the operand staging behind the VQ (FEMASR_FAST_SILU=0: exact)
   std::vector<ProfRec> prof;
   std::string prof_json;
@@ -574,7 +575,8 @@ struct Ctx {
       const float *ow = P("out_conv.weight"), *ob = P("out_conv.bias");
       const float* d2 = t;
       run("out_conv", 2.0 * 9 * 64 * 3 * (double)B * 64 * h * w,
-          [&] { return femasr_out_conv3x3(d2, ow, ob, y_nchw, B, 8 * h, 8 * w, 64, st); });
+          [&] { return net->cfg.gemm_path == 1 && net->oc_mma ? femasr_out_conv3x3_mma(d2, ow, ob, y_nchw, B, 8 * h, 8 * w, 64, st)
+                                                               : femasr_out_conv3x3(d2, ow, ob, y_nchw, B, 8 * h, 8 * w, 64, st); });
     }
     ar.release(t);
   }
@@ -726,6 +728,7 @@ extern "C" int femasr_net_create(const femasr_net_config* cfg, femasr_net** out)
   n->hq = cfg->scale_factor == 1;
   if (const char* ev = getenv("FEMASR_TC_PRECISE")) n->tc_precise = atoi(ev) != 0;
   if (const char* ev = getenv("FEMASR_FAST_SILU")) n->fast_silu = atoi(ev) != 0;
+  if (const char* ev = getenv("FEMASR_OUTCONV_MMA")) n->oc_mma = atoi(ev) != 0;
   build_spec(n);
   *out = n;
   return FEMASR_OK;

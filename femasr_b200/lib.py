@@ -103,6 +103,7 @@ SIGNATURES = {
     "femasr_in_conv4x4": (_I, [_V, _V, _V, _V, _I, _I, _I, _I, _I, _V]),
     "femasr_in_conv4x4_split": (_I, [_V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _V]),
     "femasr_out_conv3x3": (_I, [_V, _V, _V, _V, _I, _I, _I, _I, _V]),
+    "femasr_out_conv3x3_mma": (_I, [_V, _V, _V, _V, _I, _I, _I, _I, _V]),
     "femasr_nchw_to_nhwc": (_I, [_V, _V, _I, _I, _I, _I, _V]),
     "femasr_nhwc_to_nchw": (_I, [_V, _V, _I, _I, _I, _I, _V]),
 }

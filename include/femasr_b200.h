@@ -282,6 +282,10 @@ int femasr_in_conv4x4_split(const float* x_nchw, const float* w, const float* bi
 /* out_conv (femasr_arch.py:273): 3x3 pad 1, NHWC [B,H,W,Cin] -> NCHW [B,3,H,W].  w packed [9*Cin][3]. */
 int femasr_out_conv3x3(const float* x_nhwc, const float* w, const float* bias, float* y_nchw, int B,
                        int H, int W, int Cin, void* stream);
+/* Same contract on warp-level tensor cores (mma.sync, 3-term split fp16; the three horizontal taps folded into N):
+ * fp32-grade accuracy (not ATen-identical rounding), used by gemm_path 1. */
+int femasr_out_conv3x3_mma(const float* x_nhwc, const float* w, const float* bias, float* y_nchw, int B,
+                           int H, int W, int Cin, void* stream);
 
 /* layout helpers for tests */
 int femasr_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, void* stream);

@@ -42,3 +42,11 @@ x = torch.randn(B, H, W, C, device=dev)
 g, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
 ms = timeit(lambda: L.check(lib.femasr_tc_prepare(G.p(x), G.p(oh), G.p(ol), L.PRO_LN, None, None, G.p(g), G.p(b), B, H, W, C, 0, 1e-5, G.S())))
 print(f"tc_prepare LN: {ms:.3f} ms  {x.numel() * 8 / ms / 1e6:.0f} GB/s")
+
+xo = torch.randn(32, 512, 512, 64, device=dev)
+wo = torch.randn(9 * 64 * 3, device=dev) * 0.05
+bo = torch.randn(3, device=dev)
+yo = torch.empty(32, 3, 512, 512, device=dev)
+for name, fn in (("out_conv SIMT", lib.femasr_out_conv3x3), ("out_conv mma", lib.femasr_out_conv3x3_mma)):
+    ms = timeit(lambda: L.check(fn(G.p(xo), G.p(wo), G.p(bo), G.p(yo), 32, 512, 512, 64, G.S())), reps=3)
+    print(f"{name} 32x512x512x64 -> 3: {ms:.3f} ms  {(xo.numel() + yo.numel()) * 4 / ms / 1e6:.0f} GB/s")

@@ -201,6 +201,15 @@ def test_in_conv_out_conv(cuda):
     xg, wp, bg = G.nhwc(x).to(cuda), G.pack_weight(w.to(cuda)), b.to(cuda)
     L.check(lib.femasr_out_conv3x3(xg.data_ptr(), wp.data_ptr(), bg.data_ptr(), y.data_ptr(), B, 21, 130, 64, G.S()))
     close(y, want, 2e-5, "out_conv")
+    # tensor-core variant (mma.sync, split fp16, horizontal taps folded into N): ragged sizes around the 8x30 tile
+    for (Hh, Ww) in ((21, 130), (8, 30), (9, 31), (5, 7), (64, 64)):
+        x2 = rnd(B, 64, Hh, Ww, seed=33, scale=1.5)
+        want2 = F.conv2d(x2.double(), w.double(), b.double(), padding=1)
+        y2 = torch.full((B, 3, Hh, Ww), float("nan"), device=cuda)
+        x2g = G.nhwc(x2).to(cuda)
+        L.check(lib.femasr_out_conv3x3_mma(x2g.data_ptr(), wp.data_ptr(), bg.data_ptr(), y2.data_ptr(), B, Hh, Ww, 64, G.S()))
+        err = (y2.cpu().double() - want2).abs().max().item()
+        assert err <= 5e-6 * want2.abs().max().item(), f"out_conv_mma {Hh}x{Ww}: max-abs {err:.3e}"
 
 
 def test_flip_pad_copy_window_layouts(cuda):
