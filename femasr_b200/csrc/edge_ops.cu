@@ -310,20 +310,32 @@ __global__ void __launch_bounds__(OM_TH * 32, 2) out_conv_mma_kernel(const float
   uint8_t* plane_lo = om_smem + OM_PLANE;
   float* qs_all = reinterpret_cast<float*>(om_smem + 2 * OM_PLANE);
   const int x0 = blockIdx.x * OM_TW - 1, y0 = blockIdx.y * OM_TH - 1, b = blockIdx.z;     // halo origin
-  // stage the (TH+2) x 32 halo pixels as split fp16: 16 consecutive threads fetch one pixel's 256 bytes
-  for (int i = threadIdx.x; i < (OM_TH + 2) * OM_PX * (OC_CIN / 4); i += OM_TH * 32) {
-    const int c4 = i & 15, pp = i >> 4;
-    const int px = pp & (OM_PX - 1), py = pp >> 5;
-    const int gy = y0 + py, gx = x0 + px;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-      v = __ldg(reinterpret_cast<const float4*>(x + (((long)b * H + gy) * W + gx) * OC_CIN) + c4);
-    uint32_t h0, l0, h1, l1;
-    oc_split2(v.x, v.y, h0, l0);
-    oc_split2(v.z, v.w, h1, l1);
-    const int off = pp * OM_PB + c4 * 8;
-    *reinterpret_cast<uint2*>(plane_hi + off) = make_uint2(h0, h1);
-    *reinterpret_cast<uint2*>(plane_lo + off) = make_uint2(l0, l1);
+  // stage the (TH+2) x 32 halo pixels as split fp16: 16 consecutive threads fetch one pixel's 256 bytes; the loads of
+  // a batch are all issued before the first conversion (the loop is otherwise one DRAM latency per iteration)
+  constexpr int NIT = (OM_TH + 2) * OM_PX * (OC_CIN / 4) / (OM_TH * 32), UB = 5;
+  static_assert(NIT % UB == 0 && NIT * OM_TH * 32 == (OM_TH + 2) * OM_PX * (OC_CIN / 4), "staging loop shape");
+#pragma unroll 1
+  for (int it = 0; it < NIT; it += UB) {
+    float4 v[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int i = threadIdx.x + (it + u) * (OM_TH * 32);
+      const int c4 = i & 15, pp = i >> 4;
+      const int gy = y0 + (pp >> 5), gx = x0 + (pp & (OM_PX - 1));
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+        v[u] = __ldg(reinterpret_cast<const float4*>(x + (((long)b * H + gy) * W + gx) * OC_CIN) + c4);
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int i = threadIdx.x + (it + u) * (OM_TH * 32);
+      uint32_t h0, l0, h1, l1;
+      oc_split2(v[u].x, v[u].y, h0, l0);
+      oc_split2(v[u].z, v[u].w, h1, l1);
+      const int off = (i >> 4) * OM_PB + (i & 15) * 8;
+      *reinterpret_cast<uint2*>(plane_hi + off) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(plane_lo + off) = make_uint2(l0, l1);
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, cq = lane & 3;
