@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -221,6 +222,17 @@ struct Ctx {
     }
   }
 
+  // FEMASR_PROFILE_DETAIL=1: per-shape kernel labels in the profile ("tc_igemm:k3:64->64@512x512"); the strings are
+  // interned for the life of the process because the profile records keep only the pointer
+  const char* detail_name(const char* base, int k, int Cin, int Cout, int H, int W, int up, int stride, int slice) {
+    static const bool detail = [] { const char* e = getenv("FEMASR_PROFILE_DETAIL"); return e && atoi(e) != 0; }();
+    if (!detail || !net->profile) return base;
+    static std::set<std::string> names;
+    std::string s = std::string(base) + ":k" + std::to_string(k) + ":" + std::to_string(Cin) + "->" + std::to_string(Cout) + "@" +
+                    std::to_string(H) + "x" + std::to_string(W) + (up ? ":up" : "") + (stride == 2 ? ":s2" : "") + (slice ? ":sliced" : "");
+    return names.insert(s).first->c_str();
+  }
+
   const float* P(const std::string& name) {      // packed (or raw when there is no packed form)
     if (dry()) return nullptr;
     auto it = net->packed.find(name);
@@ -294,7 +306,7 @@ struct Ctx {
         // behind the VQ (bar: 1e-3 on the output) the SiLU uses the approximate exp/reciprocal units
         const int pmode = (prologue == FEMASR_PRO_GN_SILU && !precise && !precise_region && net->fast_silu)
                               ? FEMASR_PRO_GN_SILU_FAST : prologue;
-        run("tc_prepare", 0.0, [&] {
+        run(detail_name("tc_prepare", pmode, Cin, Cin, Hin, Win, 0, 1, 0), 0.0, [&] {
           return femasr_tc_prepare(x, ahi, alo, pmode, pa, pb, gamma, beta, B, Hin, Win, Cin, 0,
                                    prologue == FEMASR_PRO_LN ? 1e-5f : 1e-6f, st);
         });
@@ -317,7 +329,8 @@ struct Ctx {
         // is folded into an fp32 round-to-nearest running sum held in TMEM (see femasr_tc_args.slice_kb)
         t.slice_kb = slice;
       }
-      run("tc_igemm", flops, [&] { return femasr_tc_igemm(&t, st); });
+      run(detail_name("tc_igemm", ksize, Cin, Cout, Hin, Win, upsample, stride, t.slice_kb), flops,
+          [&] { return femasr_tc_igemm(&t, st); });
     }
     if (alo) ar.release(alo);
     if (ahi) ar.release(ahi);

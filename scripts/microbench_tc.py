@@ -30,7 +30,7 @@ STRIP = int(os.environ.get('MB_STRIP', '-1'))
 ONLY = os.environ.get('MB_ONLY', '')        # substring filter on the case name
 
 
-def conv_case(name, B, H, W, Cin, Cout, ksize=3, up=0, res=False, act=0, split=False, bias=True):
+def conv_case(name, B, H, W, Cin, Cout, ksize=3, up=0, res=False, act=0, split=False, bias=True, slice_kb=0):
     if ONLY and ONLY not in name:
         return 0.0
     hi = (torch.randn(B, H, W, Cin, device=dev) * 0.5).half()
@@ -41,7 +41,7 @@ def conv_case(name, B, H, W, Cin, Cout, ksize=3, up=0, res=False, act=0, split=F
     u = 2 if up else 1
     y = None if split else torch.empty(B, H * u, W * u, Cout, device=dev)
     r = torch.randn(B, H * u, W * u, Cout, device=dev) if res else None
-    fn = lambda: G.tc_igemm(hi, lo, blob, b, Cout, ksize, act=act, res1=r, y=y, upsample=up, split_out=split, pair=PAIR, strip=STRIP)
+    fn = lambda: G.tc_igemm(hi, lo, blob, b, Cout, ksize, act=act, res1=r, y=y, upsample=up, split_out=split, pair=PAIR, strip=STRIP, slice_kb=slice_kb)
     ms = timeit(fn)
     flops = 2.0 * B * H * u * W * u * Cout * Cin * ksize * ksize
     execd = 3 * 2.0 * B * H * W * Cout * Cin * (4 * 4 if up else ksize * ksize)
@@ -57,6 +57,9 @@ conv_case("fc1 256->1024 gelu fp32 out", 1, 1, M, 256, 1024, 1, act=1)
 conv_case("fc1 256->1024 gelu split out", 1, 1, M, 256, 1024, 1, act=1, split=True)
 conv_case("fc1 256->1024 noact fp32 out", 1, 1, M, 256, 1024, 1, act=0)
 conv_case("fc2 1024->256 +res", 1, 1, M, 1024, 256, 1, res=True)
+print("# K-sliced accumulation (layers in front of the VQ): accumulator folded into an fp32 running sum every 256 of K")
+conv_case("fc2 1024->256 +res sliced", 1, 1, M, 1024, 256, 1, res=True, slice_kb=4)
+conv_case("conv 256->256 @64x64 +res sliced", 32, 64, 64, 256, 256, res=True, slice_kb=4)
 print("# 3x3 convs, batch 32")
 conv_case("conv 256->256 @64x64 +res", 32, 64, 64, 256, 256, res=True)
 conv_case("conv 256->256 @128x128 +res", 32, 128, 128, 256, 256, res=True)
