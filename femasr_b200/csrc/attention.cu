@@ -234,10 +234,12 @@ __global__ void __launch_bounds__(128) window_attention_mma_kernel(const float* 
   m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
   m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
   float sum0 = 0.f, sum1 = 0.f;
+  constexpr float L2E = 1.4426950408889634f;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    s[nt][0] = __expf(s[nt][0] - m0); s[nt][1] = __expf(s[nt][1] - m0);
-    s[nt][2] = __expf(s[nt][2] - m1); s[nt][3] = __expf(s[nt][3] - m1);
+    // exp(x - m) = 2^(x*log2e - m*log2e): one FFMA + one MUFU.EX2 per element
+    s[nt][0] = ex2_approx_ftz(fmaf(s[nt][0], L2E, -m0 * L2E)); s[nt][1] = ex2_approx_ftz(fmaf(s[nt][1], L2E, -m0 * L2E));
+    s[nt][2] = ex2_approx_ftz(fmaf(s[nt][2], L2E, -m1 * L2E)); s[nt][3] = ex2_approx_ftz(fmaf(s[nt][3], L2E, -m1 * L2E));
     sum0 += s[nt][0] + s[nt][1];
     sum1 += s[nt][2] + s[nt][3];
   }

@@ -44,17 +44,22 @@ __device__ __forceinline__ float gelu_erf_f(float v) { return 0.5f * v * (1.0f +
 // Branch-free exact-erf GELU for hot epilogues: erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7), measured
 // max abs error of the whole GELU vs fp64 4.7e-7 on [-8,8] (ATen's own fp32 GELU: 1.2e-6); ~2.5x cheaper than
 // erff(), whose two-branch implementation diverges inside a warp.
+// single-instruction MUFU forms (the __expf / __fdividef intrinsics add ~10 instructions of denormal handling each when
+// the file is not compiled with -ftz; inputs here are never denormal-sensitive)
+__device__ __forceinline__ float ex2_approx_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// 15 instructions (2 MUFU):  gelu(v) = max(v,0) - |v|/2 * q,  q = 1 - erf(|v|/sqrt2) = poly(t) * t * exp(-z^2)
 __device__ __forceinline__ float gelu_erf_fast_f(float v) {
-  const float z = v * 0.70710678118654752440f;
-  const float az = fabsf(z);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
+  const float az = fabsf(v) * 0.70710678118654752440f;
+  const float t = rcp_approx_ftz(fmaf(0.3275911f, az, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float e = __expf(-az * az);
-  const float erf_abs = fmaf(-p * t, e, 1.0f);
-  return 0.5f * v * (1.0f + copysignf(erf_abs, z));
+  const float e = ex2_approx_ftz(az * az * -1.4426950408889634f);
+  const float q = p * t * e;
+  return fmaf(-0.5f * fabsf(v), q, fmaxf(v, 0.0f));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
