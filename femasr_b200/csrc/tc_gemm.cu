@@ -250,7 +250,10 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
-template <int BN, bool PAIR, bool STRIP, bool BRES>
+// RES: the layer adds a residual tile (res1) in the epilogue.  A template parameter because the prefetched residual
+// chunks cost 32 registers per epilogue thread and the 640-thread CTA is capped at 96: the half of the layers
+// without a residual (qkv, fc1, the first conv of every ResBlock, up / down convs) get a spill-free epilogue.
+template <int BN, bool PAIR, bool STRIP, bool BRES, bool RES>
 __global__ void __launch_bounds__(tc_threads_for(BN), 1)
 tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcP p) {
@@ -536,7 +539,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
       for (int it = 0; it < 4; ++it) { const long o = __shfl_sync(0xffffffffu, myoff, it * 8 + rsub); offs[it] = o < 0 ? -1 : o + 4 * q; }
       float4 cur[4], nxt[4];
-      if (p.res1) {
+      if (RES) {
 #pragma unroll
         for (int it = 0; it < 4; ++it)
           cur[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.res1 + offs[it]) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -570,7 +573,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll 1
       for (int ci = 0; ci < NCH; ++ci) {
         const int c = ci * CH;
-        if (p.res1 && ci + 1 < NCH) {
+        if (RES && ci + 1 < NCH) {
           // next chunk's residual, requested a whole chunk ahead (DRAM latency ~ one chunk of epilogue work)
 #pragma unroll
           for (int it = 0; it < 4; ++it)
@@ -604,7 +607,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           if (offs[it] >= 0) {
             const long off = offs[it] + c;
             float4 o = *reinterpret_cast<const float4*>(&stage[rr * 16 + 4 * (q ^ ((rr >> 1) & 3))]);
-            if (p.res1) { o.x += cur[it].x; o.y += cur[it].y; o.z += cur[it].z; o.w += cur[it].w; }
+            if (RES) { o.x += cur[it].x; o.y += cur[it].y; o.z += cur[it].z; o.w += cur[it].w; }
             if (p.res2) {
               const float4 rv = *reinterpret_cast<const float4*>(p.res2 + off);
               o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
@@ -649,7 +652,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         }
         __syncwarp();
 #pragma unroll
-        for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
+        for (int it = 0; it < 4; ++it) if (RES) cur[it] = nxt[it];
       }
       tc_fence_before();
       release_acc(acc);                         // 256 (512 when paired) arrivals release the accumulator
@@ -894,18 +897,18 @@ static int sm_count() {
   return g_sm_count;
 }
 
-template <int BN, bool PAIR, bool STRIP, bool BRES = false>
-static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-                     const TcP& p, cudaStream_t st) {
+template <int BN, bool PAIR, bool STRIP, bool BRES, bool RES>
+static int launch_tc_v(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                       const TcP& p, cudaStream_t st) {
   using Cfg = TcCfg<BN, PAIR, STRIP, BRES>;
   static bool attr_set = false;
   if (!attr_set) {
-    FEMASR_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<BN, PAIR, STRIP, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    FEMASR_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<BN, PAIR, STRIP, BRES, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   if constexpr (!PAIR) {
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    tc_igemm_kernel<BN, false, STRIP, BRES><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
+    tc_igemm_kernel<BN, false, STRIP, BRES, RES><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
     return launch_status("tc_igemm_kernel");
   } else {
     const int num_m = p.num_tiles / p.n_tiles;
@@ -918,9 +921,16 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    FEMASR_CUDA(cudaLaunchKernelEx(&cfg, tc_igemm_kernel<BN, true, false, false>, ah, al, bh, bl, p));
+    FEMASR_CUDA(cudaLaunchKernelEx(&cfg, tc_igemm_kernel<BN, true, false, false, RES>, ah, al, bh, bl, p));
     return launch_status("tc_igemm_kernel(pair)");
   }
+}
+
+template <int BN, bool PAIR, bool STRIP, bool BRES = false>
+static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                     const TcP& p, cudaStream_t st) {
+  return p.res1 ? launch_tc_v<BN, PAIR, STRIP, BRES, true>(ah, al, bh, bl, p, st)
+                : launch_tc_v<BN, PAIR, STRIP, BRES, false>(ah, al, bh, bl, p, st);
 }
 
 }  // namespace femasr
