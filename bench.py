@@ -164,6 +164,18 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
+    # stdout carries exactly ONE JSON line (rank 0).  Everything else this process or its libraries write to fd 1 - NCCL's
+    # version banner (printed at NCCL_DEBUG=VERSION and WARN), logger output - is sent to stderr: fd 1 is re-pointed at
+    # stderr for the whole run and the JSON line goes to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+    def emit(line: dict):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -185,7 +197,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": info, "gpu_launches": 0,
                 "e2e": {"value": info["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ B200 arm
@@ -200,8 +212,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
     gemm_path = args.gemm_path if args.gemm_path is not None else default_gemm_path()
 
@@ -318,7 +328,7 @@ def main():
         line["cpu_baseline"] = info
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
