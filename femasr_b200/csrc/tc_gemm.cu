@@ -47,6 +47,18 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok;
 }
+// Same with a suspend-time hint: the warp may stay parked (off the issue slots) until the phase completes or `ns`
+// elapse.  ncu showed 19 % of this kernel's executed instructions were poll iterations of the 16 epilogue warps, which
+// compete with the epilogue's own (issue-bound) work.
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+  return ok;
+}
 // Bounded wait: a protocol bug must not hang the GPU; after 4 s the kernel traps (reported as a
 // CUDA error by the next API call) instead of spinning forever.
 __device__ __forceinline__ uint64_t global_ns() {
@@ -54,11 +66,14 @@ __device__ __forceinline__ uint64_t global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#ifndef FEMASR_MBAR_HINT_NS
+#define FEMASR_MBAR_HINT_NS 20000u
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = global_ns();
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!(FEMASR_MBAR_HINT_NS ? mbar_try_wait_hint(bar, parity, FEMASR_MBAR_HINT_NS) : mbar_try_wait(bar, parity))) {
     if ((++spins & 0xFFFu) == 0 && global_ns() - t0 > 4000000000ull) {   // 4 s: far beyond any legitimate wait
       printf("femasr tc_gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
