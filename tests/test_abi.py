@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for n in names:
         assert hasattr(dll, n), f"{n} declared in the header but not exported"
     assert sorted(lib.SIGNATURES) == names, "femasr_b200/lib.py SIGNATURES out of sync with the header"
-    assert lib.load().femasr_abi_version() == 2
+    assert lib.load().femasr_abi_version() == lib.ABI_VERSION == 2
 
 
 def test_argument_validation_without_gpu(built_lib):
@@ -108,3 +108,10 @@ def test_module_copy_and_checkpoint_roundtrip(tmp_path):
     assert not missing.missing_keys and not missing.unexpected_keys
     for k, v in net.state_dict().items():
         assert torch.equal(v, other.state_dict()[k])
+
+
+def test_graft_entry_build_runs():
+    """The driver's build check: __graft_entry__.build() must compile the library and import the package (CPU only)."""
+    import importlib
+    ge = importlib.import_module("__graft_entry__")
+    ge.build()
