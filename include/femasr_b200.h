@@ -283,7 +283,10 @@ int femasr_in_conv4x4_split(const float* x_nchw, const float* w, const float* bi
 int femasr_out_conv3x3(const float* x_nhwc, const float* w, const float* bias, float* y_nchw, int B,
                        int H, int W, int Cin, void* stream);
 /* Same contract on warp-level tensor cores (mma.sync, 3-term split fp16; the three horizontal taps folded into N):
- * fp32-grade accuracy (not ATen-identical rounding), used by gemm_path 1. */
+ * fp32-grade accuracy (not ATen-identical rounding), used by gemm_path 1.
+ * Both out_conv entry points stage the 1728 weights in library-global device memory (`__constant__` / fragment
+ * buffer) that is refreshed by every call in stream order: calls issued on DIFFERENT streams must not overlap
+ * (one engine handle = one host thread = one stream at a time, see the threading note in INTEGRATION.md). */
 int femasr_out_conv3x3_mma(const float* x_nhwc, const float* w, const float* bias, float* y_nchw, int B,
                            int H, int W, int Cin, void* stream);
 
