@@ -1,21 +1,30 @@
-"""`build_network(opt)` over ARCH_REGISTRY (reference: basicsr/archs/__init__.py:13-25)."""
-import importlib
-import os
-from copy import deepcopy
+"""Network factory of the drop-in surface: `build_network({"type": <registered class name>, **kwargs})`.
+
+Plays the role of the reference's basicsr/archs/__init__.py:13-25 - architectures register themselves in
+ARCH_REGISTRY when their module is imported, the factory looks the class up by name."""
+import copy
+import pkgutil
+from importlib import import_module
 
 from basicsr.utils import get_root_logger
 from basicsr.utils.registry import ARCH_REGISTRY
 
 __all__ = ["build_network"]
 
-# every `*_arch.py` next to this file registers its classes on import
-for _f in sorted(os.listdir(os.path.dirname(os.path.abspath(__file__)))):
-    if _f.endswith("_arch.py"):
-        importlib.import_module(f"basicsr.archs.{_f[:-3]}")
+
+def _register_architectures():
+    """Import every sibling module named *_arch (each one decorates its classes with ARCH_REGISTRY.register())."""
+    for info in pkgutil.iter_modules(__path__):
+        if info.name.endswith("_arch"):
+            import_module(f"{__name__}.{info.name}")
+
+
+_register_architectures()
 
 
 def build_network(opt):
-    opt = deepcopy(opt)
-    net = ARCH_REGISTRY.get(opt.pop("type"))(**opt)
-    get_root_logger().info(f"Network [{net.__class__.__name__}] is created.")
-    return net
+    kwargs = copy.deepcopy(dict(opt))
+    cls = ARCH_REGISTRY.get(kwargs.pop("type"))
+    network = cls(**kwargs)
+    get_root_logger().info("Network [%s] is created." % type(network).__name__)
+    return network
