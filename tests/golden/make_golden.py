@@ -49,6 +49,16 @@ CASES = [
 ]
 
 
+# constructor flags (femasr_arch.py:224,226,349-350,361-362): pinned for the ORACLE only (tests/golden/cpu_only/, read by
+# tests/test_oracle.py); the CUDA path is compared with the oracle for these flags in tests/test_net_gpu.py
+CPU_ONLY_CASES = [
+    ("x4_e256_noresidual_fwd", 4, 256, "perturbed", 25, "forward", (1, 3, 32, 32), {"ctor": {"use_residual": False}}),
+    ("x4_e256_noquant_fwd", 4, 256, "perturbed", 26, "forward", (1, 3, 32, 32), {"ctor": {"use_quantize": False}}),
+    ("x4_ms2_noquant_fwd", 4, 256, "perturbed", 27, "forward", (1, 3, 32, 32),
+     {"codebooks": [[32, 1024, 256], [64, 512, 128]], "ctor": {"use_quantize": False}}),
+]
+
+
 def sd_digest(sd) -> str:
     h = hashlib.sha256()
     for k in sorted(sd):
@@ -66,19 +76,21 @@ def main():
     ref = import_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     only = set(sys.argv[1:])
-    for name, scale, e_dim, init, seed, entry, shape, extra in CASES:
+    for name, scale, e_dim, init, seed, entry, shape, extra in CASES + CPU_ONLY_CASES:
         if only and name not in only:
             continue
         extra = dict(extra)
+        ctor = extra.pop("ctor", {})
         cbs = extra.pop("codebooks", [[32, 1024, e_dim]])
         use_gt = extra.pop("gt", False)
         sd = random_state_dict(scale, e_dim, seed=seed, init=init, codebooks=cbs)
-        net = ref.FeMaSRNet(codebook_params=cbs, LQ_stage=scale != 1, scale_factor=scale).eval()
+        net = ref.FeMaSRNet(codebook_params=cbs, LQ_stage=scale != 1, scale_factor=scale, **ctor).eval()
         net.load_state_dict(sd, strict=True)
         g = torch.Generator().manual_seed(1000 + seed)
         rec = dict(scale=scale, e_dim=e_dim, init=init, seed=seed, entry=entry, digest=sd_digest(sd),
                    codebooks=np.array(cbs, dtype=np.int64))
         rec.update({f"arg_{k}": v for k, v in extra.items()})
+        rec.update({f"ctor_{k}": v for k, v in ctor.items()})
         taps = {}
         d = encode_depth(scale)
         hooks = []
@@ -125,7 +137,9 @@ def main():
         rec.update(input=x.numpy(), out=out.numpy())
         if entry == "forward":
             rec.update({f"tap_{k}": sample(v) for k, v in taps.items()})
-        path = os.path.join(OUT, name + ".npz")
+        sub = os.path.join(OUT, "cpu_only") if ctor else OUT
+        os.makedirs(sub, exist_ok=True)
+        path = os.path.join(sub, name + ".npz")
         np.savez_compressed(path, **rec)
         print(f"{name}: out {tuple(out.shape)} |out|max {out.abs().max():.3f}  -> {os.path.getsize(path) / 1e3:.0f} kB")
 

@@ -60,6 +60,33 @@ def test_oracle_matches_reference_golden(path):
     np.testing.assert_allclose(out.numpy(), g["out"], rtol=0, atol=1e-5)
 
 
+import glob as _glob
+import os as _os
+
+CPU_ONLY = sorted(_glob.glob(_os.path.join(_os.path.dirname(__file__), "golden", "cpu_only", "*.npz")))
+
+
+@pytest.mark.parametrize("path", CPU_ONLY, ids=[_os.path.basename(p)[:-4] for p in CPU_ONLY])
+def test_oracle_constructor_flags_match_reference(path):
+    """use_residual=False / use_quantize=False (femasr_arch.py:224,226,349-350,361-362), pinned for the oracle; the CUDA
+    path is compared with the oracle for these flags in tests/test_net_gpu.py."""
+    g, sd, cbs = load_case(path)
+    assert digest(sd) == str(g["digest"])
+    flags = {k[5:]: bool(g[k]) for k in g.files if k.startswith("ctor_")}
+    assert flags, "cpu_only fixtures carry constructor flags"
+    with torch.no_grad():
+        out, loss, sem, idx = O.encode_and_decode(sd, torch.from_numpy(g["input"]), int(g["scale"]),
+                                                  cb_scales=[c[0] for c in cbs], **flags)
+    for a, b in zip(idx, indices_of(g)):
+        assert np.array_equal(a.numpy(), b)
+    np.testing.assert_allclose(loss.numpy(), g["loss"], rtol=1e-6)
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=0, atol=1e-5)
+
+
+def test_cpu_only_goldens_present():
+    assert len(CPU_ONLY) == 3
+
+
 def test_flop_model_matches_survey():
     assert abs(O.flops_per_image(4, 128, 128, 256) / 1e9 - 754.53) < 0.01
     assert abs(O.flops_per_image(4, 128, 128, 512) / 1e9 - 762.05) < 0.01
