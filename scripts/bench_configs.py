@@ -12,7 +12,20 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from basicsr.archs import build_network  # noqa: E402
 from femasr_b200.spec import random_state_dict  # noqa: E402
-from oracle.femasr_oracle import flops_per_image  # noqa: E402
+
+
+def flops_per_image(scale, h, w, e_dim):
+    """Algorithmic FLOPs of one forward from the engine's own model (femasr_net_flops; no oracle import here)."""
+    import ctypes as C
+    from femasr_b200 import lib as L
+    lib = L.load()
+    cfg = L.NetConfig(scale, 1024, e_dim, 3, 1, 1, 1, 0, (C.c_int * 3)(), (C.c_int * 3)(), (C.c_int * 3)())
+    hnd = C.c_void_p()
+    L.check(lib.femasr_net_create(C.byref(cfg), C.byref(hnd)))
+    try:
+        return float(lib.femasr_net_flops(hnd, 1, h, w))
+    finally:
+        lib.femasr_net_destroy(hnd)
 
 dev = torch.device("cuda", 0)
 
