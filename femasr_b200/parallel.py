@@ -8,7 +8,7 @@ The reference has no multi-GPU inference path (basicsr/models/femasr_model.py:22
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -61,3 +61,44 @@ def sharded_forward(run: Callable[[torch.Tensor], torch.Tensor], x_global: torch
             raise ValueError("an empty shard needs out_shape_fn to size its (empty) output")
         local = x_global.new_zeros((0,) + tuple(out_shape_fn(x_global.shape)[1:]))
     return all_gather_outputs(local, counts, group)
+
+
+def tile_classes(height: int, width: int, tile_size: int, tile_pad: int) -> Dict[Tuple[int, int], List[dict]]:
+    """The tiles of FeMaSRNet.test_tile (femasr_arch.py:387-447) grouped by the shape of their padded input window:
+    tiles of one class can be stacked into one batch.  Deterministic order (row-major inside a class)."""
+    from .net import tile_plan                      # pure Python (no CUDA needed to plan)
+    classes: Dict[Tuple[int, int], List[dict]] = {}
+    for t in tile_plan(height, width, tile_size, tile_pad):
+        py0, py1, px0, px1 = t["in"]
+        classes.setdefault((py1 - py0, px1 - px0), []).append(t)
+    return classes
+
+
+def sharded_test_tile(run: Callable[[torch.Tensor], torch.Tensor], x: torch.Tensor, scale: int, tile_size: int,
+                      tile_pad: int, rank: int, world: int, group: Optional[dist.ProcessGroup] = None,
+                      max_batch: int = 64) -> torch.Tensor:
+    """test_tile with the TILE LIST sharded over the ranks: inside every same-shape class the tiles are
+    dealt round-robin, each rank runs `run` (e.g. FeMaSRNet.test) on stacks of its tiles, one all-gather per class
+    brings the SR tiles to every rank, and every rank pastes the full [B,3,sH,sW] result.  `run` maps
+    [n,3,th,tw] -> [n,3,s*th,s*tw]; tiles are independent on this path, so stacking does not change their values."""
+    B, C, H, W = x.shape
+    s = scale
+    out = x.new_zeros((B, C, H * s, W * s))
+    for (th, tw), tiles in tile_classes(H, W, tile_size, tile_pad).items():
+        mine = tiles[rank::world]
+        counts = [len(tiles[r::world]) * B for r in range(world)]
+        parts = []
+        per = max(1, max_batch // B)
+        for i in range(0, len(mine), per):
+            chunk = mine[i:i + per]
+            stack = torch.cat([x[:, :, t["in"][0]:t["in"][1], t["in"][2]:t["in"][3]] for t in chunk], 0)
+            parts.append(run(stack.contiguous()))
+        local = torch.cat(parts, 0) if parts else x.new_zeros((0, C, th * s, tw * s))
+        full = all_gather_outputs(local, counts, group)          # rank-major: rank 0's tiles, rank 1's tiles, ...
+        order = [t for r in range(world) for t in tiles[r::world]]
+        for k, t in enumerate(order):
+            y0, y1, x0, x1 = t["out"]
+            cy, cx = t["crop"]
+            sr = full[k * B:(k + 1) * B]
+            out[:, :, y0 * s:y1 * s, x0 * s:x1 * s] = sr[:, :, cy * s:(cy + y1 - y0) * s, cx * s:(cx + x1 - x0) * s]
+    return out

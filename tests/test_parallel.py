@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from femasr_b200.parallel import all_gather_outputs, shard_counts, shard_range, sharded_forward
+from femasr_b200.parallel import (all_gather_outputs, shard_counts, shard_range, sharded_forward, sharded_test_tile,
+                                  tile_classes)
 
 
 def test_shard_ranges_partition_the_batch():
@@ -52,3 +53,48 @@ def test_world2_gloo_gather(n):
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, n, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def _stub_tile_sr(t):                  # a per-pixel "SR" (x4 nearest) so that tiling + paste must reproduce the whole image
+    return t.repeat_interleave(4, 2).repeat_interleave(4, 3) * 3.0 - 0.5
+
+
+def _tile_worker(rank, world, port, shape, ts, tp, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x = torch.rand(shape, generator=torch.Generator().manual_seed(1))
+        out = sharded_test_tile(_stub_tile_sr, x, 4, ts, tp, rank, world, max_batch=4)
+        ret[rank] = bool(torch.equal(out, _stub_tile_sr(x)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape,ts,tp", [((1, 3, 72, 56), 32, 8), ((2, 3, 40, 100), 24, 4), ((1, 3, 20, 20), 32, 8)])
+def test_world2_gloo_sharded_test_tile(shape, ts, tp):
+    """Tile-list sharding: every tile runs on exactly one rank, both ranks end with the whole image."""
+    classes = tile_classes(shape[2], shape[3], ts, tp)
+    ntiles = sum(len(v) for v in classes.values())
+    assert ntiles == -(-shape[2] // ts) * -(-shape[3] // ts)
+    for tiles in classes.values():            # round-robin deal: per class the ranks differ by at most one tile
+        assert abs(len(tiles[0::2]) - len(tiles[1::2])) <= 1
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ret = mp.Manager().dict()
+    mp.spawn(_tile_worker, args=(2, port, shape, ts, tp, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
+
+
+def test_sharded_test_tile_matches_oracle_test_tile():
+    """Single process, the CPU oracle as the per-tile runner: the sharded/batched schedule equals the reference's
+    one-tile-at-a-time test_tile (femasr_arch.py:387-447)."""
+    from femasr_b200.spec import random_state_dict
+    from oracle import femasr_oracle as O
+    sd = random_state_dict(4, 256, seed=41, init="perturbed")
+    x = torch.rand((1, 3, 40, 24), generator=torch.Generator().manual_seed(42))
+    with torch.no_grad():
+        want = O.test_tile(sd, x, 4, 16, 8)
+        got = sharded_test_tile(lambda t: O.test(sd, t, 4), x, 4, 16, 8, rank=0, world=1)
+    assert (got - want).abs().max().item() <= 1e-5
