@@ -35,6 +35,29 @@ inline int launch_status(const char* what) {
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Per-device one-time state.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count belong to a DEVICE, not
+// to the process: engines on several GPUs may live in one process (the reference surface is `.to(any device)`).
+constexpr int MAX_DEVICES = 64;
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEVICES) d = 0;
+  return d;
+}
+struct PerDeviceFlag {
+  bool set[MAX_DEVICES] = {};
+  bool& cur() { return set[current_device()]; }
+};
+inline int sm_count() {
+  static int counts[MAX_DEVICES] = {};
+  const int d = current_device();
+  if (!counts[d]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+    counts[d] = n > 0 ? n : 148;
+  }
+  return counts[d];
+}
+
 __host__ __device__ inline long cdiv(long a, long b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }

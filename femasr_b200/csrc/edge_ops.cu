@@ -251,10 +251,10 @@ extern "C" int femasr_out_conv3x3(const float* x, const float* w, const float* b
   FEMASR_CUDA(cudaMemcpyToSymbolAsync(c_outconv_w, w, sizeof(float) * 9 * OC_CIN * 3, 0, cudaMemcpyDeviceToDevice, st));
   FEMASR_CUDA(cudaMemcpyToSymbolAsync(c_outconv_b, bias, sizeof(float) * 3, 0, cudaMemcpyDeviceToDevice, st));
   constexpr int smem = (OC_TH + 2) * (OC_TW + 2) * OC_PS * (int)sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  if (!attr_set.cur()) {
     FEMASR_CUDA(cudaFuncSetAttribute(out_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_set.cur() = true;
   }
   dim3 grid((unsigned)cdiv(W, OC_TW), (unsigned)cdiv(H, OC_TH), B);
   out_conv_kernel<<<grid, OC_TH * OC_TW, smem, st>>>(x, y, B, H, W);
@@ -415,10 +415,10 @@ extern "C" int femasr_out_conv3x3_mma(const float* x, const float* w, const floa
   FEMASR_CHECK_ARG(cdiv(H, OM_TH) <= 65535 && B <= 65535, "out_conv_mma: grid too large");
   cudaStream_t st = as_stream(stream);
   out_conv_bfrag_kernel<<<6, 256, 0, st>>>(w);     // stream-ordered refresh of the B fragments (several engines can coexist)
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  if (!attr_set.cur()) {
     FEMASR_CUDA(cudaFuncSetAttribute(out_conv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OM_SMEM));
-    attr_set = true;
+    attr_set.cur() = true;
   }
   dim3 grid((unsigned)cdiv(W, OM_TW), (unsigned)cdiv(H, OM_TH), B);
   out_conv_mma_kernel<<<grid, OM_TH * 32, OM_SMEM, st>>>(x, bias, y, B, H, W);

@@ -907,25 +907,14 @@ static int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t*
   return FEMASR_OK;
 }
 
-static int g_sm_count = 0;
-static int sm_count() {
-  if (!g_sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
-  }
-  return g_sm_count;
-}
-
 template <int BN, bool PAIR, bool STRIP, bool BRES, bool RES>
 static int launch_tc_v(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                        const TcP& p, cudaStream_t st) {
   using Cfg = TcCfg<BN, PAIR, STRIP, BRES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;      // per template instantiation AND per device
+  if (!attr_set.cur()) {
     FEMASR_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<BN, PAIR, STRIP, BRES, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_set.cur() = true;
   }
   if constexpr (!PAIR) {
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();

@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -69,7 +70,13 @@ class NativeNet:
                       if kind not in ("rpi", "mask")]
         # the forward is a fixed launch list per input shape: replay it as a CUDA graph (no per-launch host work)
         self.use_graph = os.environ.get("FEMASR_CUDA_GRAPH", "1") != "0"
-        self._graphs: Dict[Tuple[int, int, int], dict] = {}
+        # Captured graphs pin their workspace and static buffers (13 GB at 32x128x128), so the cache is a small LRU and
+        # a shape is captured only when it comes back: a folder of 38 differently sized images (the reference's testset)
+        # runs eagerly on the ONE shared workspace instead of accumulating 38 graphs.
+        self.graph_cache_size = max(0, int(os.environ.get("FEMASR_GRAPH_CACHE", "4")))
+        self._graphs: "OrderedDict[Tuple[int, ...], dict]" = OrderedDict()
+        self._seen_shapes: "OrderedDict[Tuple[int, ...], int]" = OrderedDict()
+        self.last_from_graph = False     # whether the last forward_graph() result lives in a graph's static buffers
 
     # ------------------------------------------------------------------ lifecycle
     def _ensure(self, device: torch.device):
@@ -162,6 +169,8 @@ class NativeNet:
                 gl = [gt_indices] if torch.is_tensor(gt_indices) else list(gt_indices)
                 if len(gl) != len(ishapes) or any(g.numel() != n for g, n in zip(gl, isizes)):
                     raise L.FemasrError(f"gt_indices must hold one map per codebook with {isizes} entries")
+                for g_, (_cs, ne_, _e) in zip(gl, self.codebooks):
+                    self._check_index_range(g_, ne_, "forward(gt_indices)")
                 gt = torch.cat([g.detach().to(self.device, torch.int64).reshape(-1) for g in gl]).contiguous()
             loss = torch.empty((), dtype=torch.float32, device=self.device) if want_loss else None
             tap_out = {}
@@ -186,13 +195,24 @@ class NativeNet:
         return y, loss, idx
 
     def forward_graph(self, x: torch.Tensor):
-        """encode_and_decode through a captured CUDA graph (one per input shape).  Returns (y, loss, idx) living in
-        the graph's static output buffers: valid until the next call with the same shape (clone to keep)."""
+        """encode_and_decode through a captured CUDA graph.  Returns (y, loss, idx); when they come out of a graph
+        they live in its static output buffers: valid until the next call with the same shape (clone to keep).
+        Policy: the first sighting of a shape runs eagerly (shared workspace); the second captures; at most
+        ``graph_cache_size`` graphs are kept (least recently used evicted, its workspace and buffers freed)."""
         self._ensure(x.device)
         x = x.detach().float().contiguous()
         key = tuple(x.shape)
         ent = self._graphs.get(key)
         if ent is None:
+            seen = self._seen_shapes.pop(key, 0) + 1
+            self._seen_shapes[key] = seen
+            while len(self._seen_shapes) > 64:
+                self._seen_shapes.popitem(last=False)
+            if seen < 2 or self.graph_cache_size == 0:
+                self.last_from_graph = False
+                return self.forward(x)
+            while len(self._graphs) >= self.graph_cache_size:
+                self._graphs.popitem(last=False)          # drops the graph, its workspace and static buffers
             with torch.cuda.device(self.device):
                 xs = torch.empty_like(x)
                 xs.copy_(x)
@@ -208,9 +228,17 @@ class NativeNet:
                 ent = {"graph": g, "x": xs, "y": y, "loss": loss, "idx": idx, "ws": self._ws}
                 self._ws = None                           # the captured launches own this workspace from now on
                 self._graphs[key] = ent
+        else:
+            self._graphs.move_to_end(key)
+        self.last_from_graph = True
         ent["x"].copy_(x, non_blocking=True)
         ent["graph"].replay()
         return ent["y"], ent["loss"], ent["idx"]
+
+    def release_graphs(self):
+        """Drop every captured graph (and the workspaces they pin)."""
+        self._graphs.clear()
+        self._seen_shapes.clear()
 
     def tap_shapes(self, B: int, H: int, W: int) -> Dict[str, Tuple[int, ...]]:
         s = self.scale
@@ -228,6 +256,7 @@ class NativeNet:
         self._ensure(indices.device)
         idx = indices.detach().to(torch.int64).contiguous()
         B, _, h, w = idx.shape
+        self._check_index_range(idx, self.n_e, "decode_indices")
         with torch.cuda.device(self.device):
             need = C.c_size_t()
             L.check(self.lib.femasr_net_decode_workspace_bytes(self._h, B, h, w, C.byref(need)))
@@ -236,6 +265,15 @@ class NativeNet:
             L.check(self.lib.femasr_net_decode_indices(self._h, idx.data_ptr(), y.data_ptr(), B, h, w,
                                                        ws.data_ptr(), ws.numel(), _stream()))
         return y
+
+    @staticmethod
+    def _check_index_range(idx: torch.Tensor, n_e: int, what: str):
+        """The reference raises on an index outside the codebook (scatter_ in get_codebook_entry / the gt one-hot,
+        femasr_arch.py:70-78,102-112); the kernels clamp for memory safety, so the range is checked here."""
+        if idx.numel():
+            lo, hi = int(idx.min()), int(idx.max())
+            if lo < 0 or hi >= n_e:
+                raise L.FemasrError(f"{what}: codebook index out of range [0, {n_e}): min {lo}, max {hi}")
 
     def set_profile(self, enable: bool):
         L.check(self.lib.femasr_net_set_profile(self._h, int(enable)))

@@ -56,6 +56,15 @@ def test_reference_entry_script_runs_unchanged_up_to_the_device(tmp_path, built_
         sys.argv = argv
 
 
+@pytest.mark.skipif(not reference_available(), reason="needs /root/reference")
+def test_fixture_is_the_reference_script():
+    """tests/fixtures/inference_femasr.py (what the GPU box executes, tests/test_reference_entry_gpu.py) must be the
+    reference's entry script byte for byte."""
+    a = open(os.path.join(ROOT, "tests", "fixtures", "inference_femasr.py"), "rb").read()
+    b = open(os.path.join(REFERENCE_ROOT, "inference_femasr.py"), "rb").read()
+    assert a == b
+
+
 @pytest.mark.gpu
 def test_demo_entry_matches_oracle_pngs(tmp_path, cuda):
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
