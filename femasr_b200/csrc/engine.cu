@@ -109,6 +109,8 @@ struct femasr_net {
   bool profile = false;
   bool tc_precise = true;                 // K-sliced fp32 accumulation for the layers in front of the VQ
   bool oc_mma = true;                     // out_conv on mma.sync in the tensor-core path (FEMASR_OUTCONV_MMA=0: SIMT kernel)
+  int tc_slice_kb = 4;                    // K-slice length in 64-wide k-blocks (FEMASR_TC_SLICE_KB; study knob)
+  bool vq_fused = true;                   // VQ distances on the tensor cores with the argmin fused (FEMASR_VQ_FUSED=0: fp32 SIMT z.E^T + vq_select)
   bool fast_silu = true;                  // approximate-unit SiLU in the operand staging behind the VQ (FEMASR_FAST_SILU=0: exact)
   std::vector<ProfRec> prof;
   std::string prof_json;
@@ -323,7 +325,7 @@ struct Ctx {
       const int Ho = stride == 2 ? (Hin - 1) / 2 + 1 : Hin * u, Wo = stride == 2 ? (Win - 1) / 2 + 1 : Win * u;
       const double flops = 2.0 * B * Ho * (double)Wo * Cout * Cin * ksize * ksize;   // algorithmic (reference) count
       const int nkb = (upsample ? 4 : ksize * ksize) * (Cin / 64);
-      const int slice = 4;                       // 4 k-blocks = 256 of K per launch
+      const int slice = net->tc_slice_kb;        // k-blocks per accumulator drain (default 4 = 256 of K)
       if ((precise || precise_region) && net->tc_precise && nkb > slice) {
         // K-sliced accumulation (layers in front of the VQ): every 256 of K the tensor core's truncating accumulator
         // is folded into an fp32 round-to-nearest running sum held in TMEM (see femasr_tc_args.slice_kb)
@@ -351,7 +353,7 @@ struct Ctx {
     memset(&t, 0, sizeof(t));
     t.B = B; t.H = H; t.W = W; t.Cin = Cin; t.Cout = Cout; t.ksize = 3; t.upsample = upsample; t.stride = stride;
     t.pair = -1; t.strip = -1;
-    t.slice_kb = (precise_region && net->tc_precise && (upsample ? 4 : 9) * (Cin / 64) > 4) ? 4 : 0;
+    t.slice_kb = (precise_region && net->tc_precise && (upsample ? 4 : 9) * (Cin / 64) > net->tc_slice_kb) ? net->tc_slice_kb : 0;
     Stats st_;
     st_.rows = femasr_tc_gn_partial_rows(&t);
     st_.partial = ar.alloc((size_t)B * st_.rows * 32 * 2);
@@ -483,8 +485,19 @@ struct Ctx {
     float* z = ar.alloc(N * e);
     conv("before_quant_group." + ks, src, z, B, hh, ww, Cin, e, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
     tap(k == 0 ? "z" : (k == 1 ? "z1" : "z2"), z, N * e);
-    float* zc = ar.alloc(N * cb.n_e);
-    conv("quantize_group." + ks + ".embedding", z, zc, B, hh, ww, e, cb.n_e, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, false);
+    const std::string cname = "quantize_group." + ks + ".embedding.weight";
+    const bool fused = net->cfg.gemm_path == 1 && net->vq_fused && (dry() || net->tcw.count(cname) != 0);
+    // fused: tensor-core distances + in-kernel top-4 (no [N, n_e] tensor); else the fp32 SIMT product + vq_select
+    float *zc = nullptr, *arow = nullptr, *zhi = nullptr, *zlo = nullptr, *cand = nullptr;
+    if (fused) {
+      arow = ar.alloc(N);
+      zhi = ar.alloc((N * e + 1) / 2);
+      zlo = ar.alloc((N * e + 1) / 2);
+      cand = ar.alloc(N * 8);
+    } else {
+      zc = ar.alloc(N * cb.n_e);
+      conv("quantize_group." + ks + ".embedding", z, zc, B, hh, ww, e, cb.n_e, 1, 1, 0, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, false);
+    }
     float* zq = ar.alloc(N * e);
     float* lrows = ar.alloc(N);
     const bool gt_loss = gt && !net->hq;                 // :84: only the LQ stage uses gt_indices for the loss
@@ -492,10 +505,17 @@ struct Ctx {
     const int gtiles = femasr_gram_diff_tiles(e);
     if (gt_loss) { zq_gt = ar.alloc(N * e); gpart = ar.alloc((size_t)B * gtiles); }
     if (!dry() && ok()) {
-      const std::string cname = "quantize_group." + ks + ".embedding.weight";
       const float* cbw = net->raw[cname].p;
       const float* esq = net->esq[cname].p;
-      run("vq_select", 0.0, [&] { return femasr_vq_select(z, zc, cbw, esq, indices, zq, lrows, (int)N, cb.n_e, e, 0, st); });
+      if (fused) {
+        const void* cbt = net->tcw[cname].p;
+        run("vq_row_sumsq", 0.0, [&] { return femasr_row_sumsq(z, arow, (int)N, e, st); });
+        run("tc_prepare", 0.0, [&] { return femasr_tc_prepare(z, zhi, zlo, FEMASR_PRO_NONE, nullptr, nullptr, nullptr, nullptr, B, hh, ww, e, 0, 0.f, st); });
+        run("vq_match_tc", 2.0 * (double)N * cb.n_e * e, [&] { return femasr_vq_match_tc(zhi, zlo, cbt, arow, esq, cand, (int)N, cb.n_e, e, st); });
+        run("vq_finish", 0.0, [&] { return femasr_vq_finish(z, arow, cand, cbw, esq, indices, zq, lrows, nullptr, (int)N, cb.n_e, e, st); });
+      } else {
+        run("vq_select", 0.0, [&] { return femasr_vq_select(z, zc, cbw, esq, indices, zq, lrows, (int)N, cb.n_e, e, 0, st); });
+      }
       if (cb_loss && !gt_loss) {
         const double s = 1.25 / ((double)N * e);         // q_latent + 0.25 * e_latent, :92
         run("sum_scaled", 0.0, [&] { return k == 0 ? femasr_sum_scaled(lrows, cb_loss, N, s, st) : femasr_sum_scaled_add(lrows, cb_loss, N, s, st); });
@@ -509,7 +529,8 @@ struct Ctx {
     }
     if (gt_loss) { ar.release(gpart); ar.release(zq_gt); }
     ar.release(lrows);
-    ar.release(zc);
+    if (fused) { ar.release(cand); ar.release(zlo); ar.release(zhi); ar.release(arow); }
+    else ar.release(zc);
     if (k == 0) tap("zq", zq, N * e);
     *z_out = z; *zq_out = zq;
   }
@@ -742,6 +763,8 @@ extern "C" int femasr_net_create(const femasr_net_config* cfg, femasr_net** out)
   if (const char* ev = getenv("FEMASR_TC_PRECISE")) n->tc_precise = atoi(ev) != 0;
   if (const char* ev = getenv("FEMASR_FAST_SILU")) n->fast_silu = atoi(ev) != 0;
   if (const char* ev = getenv("FEMASR_OUTCONV_MMA")) n->oc_mma = atoi(ev) != 0;
+  if (const char* ev = getenv("FEMASR_VQ_FUSED")) n->vq_fused = atoi(ev) != 0;
+  if (const char* ev = getenv("FEMASR_TC_SLICE_KB")) n->tc_slice_kb = std::max(1, atoi(ev));
   build_spec(n);
   *out = n;
   return FEMASR_OK;
@@ -804,7 +827,15 @@ extern "C" int femasr_net_set_param(femasr_net* net, const char* name, const flo
     if (s) return s;
     DevBuf& eb = net->esq[key];
     if (!eb.p) { FEMASR_CUDA(cudaMalloc(&eb.p, pi.Cout * sizeof(float))); eb.n = pi.Cout; }
-    return femasr_row_sumsq(rb.p, eb.p, pi.Cout, pi.Cin, st);
+    s = femasr_row_sumsq(rb.p, eb.p, pi.Cout, pi.Cin, st);
+    if (s) return s;
+    if (net->cfg.gemm_path == 1 && net->vq_fused) {     // split-fp16 planes of the [n_e, e_dim] embedding: B operand of the fused VQ
+      DevBuf& tb = net->tcw[key];
+      const size_t bytes = femasr_tc_weight_bytes(pi.Cout, pi.Cin, 1, 1);
+      if (!tb.p) { FEMASR_CUDA(cudaMalloc(&tb.p, bytes)); tb.n = bytes / sizeof(float); }
+      return femasr_tc_pack_weight(rb.p, tb.p, pi.Cout, pi.Cin, 1, 1, st);
+    }
+    return FEMASR_OK;
   }
   return FEMASR_OK;
 }

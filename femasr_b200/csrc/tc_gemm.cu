@@ -20,6 +20,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstring>
 #include <mutex>
 #include <string>
 
@@ -166,6 +167,11 @@ struct TcP {
   int slice_kb;                  // >0: in-kernel K slicing - every slice_kb k-blocks the accumulator is drained into an
                                  // fp32 running sum kept in the second TMEM buffer (round-to-nearest adds by the
                                  // epilogue warps), so the truncating MMA accumulator never runs longer than a slice
+  // VQ mode (template VQ): the GEMM is z . E^T and the epilogue keeps, per feature row, the four smallest distances
+  // fl(fl(A + B_j) - 2 C_j) over all codes instead of storing the [N, n_e] product (femasr_arch.py:35-38, 63-66)
+  const float* vq_a;             // [M]   A = sum z^2 per row
+  const float* vq_esq;           // [Cout] B_j = sum e_j^2 per code
+  uint2* vq_cand;                // [M][4] {distance bits, code}, ascending (distance, code)
 };
 
 constexpr int TC_BM = 128, TC_BK = 64;
@@ -216,8 +222,16 @@ struct TcCfg {
   static constexpr int NBAR_PIPE = BRES ? 2 * SA_STAGES + 1 : (STRIP ? 2 * SA_STAGES + 2 * SB_STAGES : 2 * STAGES);
   static constexpr int EPI_BYTES = EPI_WARPS * 2048 /*per-warp 32x16 fp32 transpose tiles*/;
   static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators; power of two for BN in {64,128,256}
-  static_assert(8 * (NBAR_PIPE + 4) + 4 <= 256, "barrier area");
+  // Multi-row strip tiles (resident weights): one work item = MR vertically adjacent image rows of 128 pixels, each its
+  // own 128 x BN accumulator.  Input row s (of MR + 2) is loaded ONCE and feeds the kh = s - r tap row of every output
+  // row r it touches, so a tile streams (MR + 2) / MR strips per output row instead of 3 (L2 -> SM traffic / 2 at MR = 4)
+  // and every strip carries 2x the MMA work, which is what hides the strip's load latency behind only two strip stages
+  // (all the shared memory the resident weights leave).
+  static constexpr int MR = BRES ? 4 : 1;
+  static constexpr int NACC = 2 * MR;                             // accumulator ring: two sets of MR
+  static constexpr int TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;   // power of two for BN in {64,128,256}
+  static_assert(TMEM_COLS <= 512, "TMEM budget");
+  static_assert(8 * (NBAR_PIPE + 2 * NACC) + 4 <= 256, "barrier area");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(!STRIP || BRES || SB_STAGES >= 2, "strip weight ring too small");
 };
@@ -268,7 +282,9 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
 // RES: the layer adds a residual tile (res1) in the epilogue.  A template parameter because the prefetched residual
 // chunks cost 32 registers per epilogue thread and the 640-thread CTA is capped at 96: the half of the layers
 // without a residual (qkv, fc1, the first conv of every ResBlock, up / down convs) get a spill-free epilogue.
-template <int BN, bool PAIR, bool STRIP, bool BRES, bool RES>
+// VQ: the z . E^T product of the VectorQuantizer with the argmin fused into the epilogue (see the VQ epilogue below);
+// work is ordered M-major so that one CTA sees ALL code tiles of its 128 feature rows back to back.
+template <int BN, bool PAIR, bool STRIP, bool BRES, bool RES, bool VQ = false>
 __global__ void __launch_bounds__(tc_threads_for(BN), 1)
 tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcP p) {
@@ -286,8 +302,9 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   auto fullB_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::SA_STAGES + s); };
   auto emptyB_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::SA_STAGES + Cfg::SB_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (Cfg::NBAR_PIPE + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (Cfg::NBAR_PIPE + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (Cfg::NBAR_PIPE + 4);
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (Cfg::NBAR_PIPE + Cfg::NACC + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (Cfg::NBAR_PIPE + 2 * Cfg::NACC);
+  constexpr int MR = Cfg::MR, NACC = Cfg::NACC;
 
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // CTA 0 of the pair issues the MMAs
   const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -299,11 +316,22 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   const int m_per_phase = num_m / phases;
   const int pairs_per_phase = (m_per_phase + 1) / 2;
   const int num_work = PAIR ? phases * pairs_per_phase * p.n_tiles : p.num_tiles;
+  static_assert(!VQ || (!PAIR && !STRIP && !RES), "VQ mode: plain single-CTA linear tiles");
+  // it-th work item of this CTA (-1: done).  Default: items strided over the CTAs.  VQ: m-tiles strided over the
+  // CTAs, and for each m-tile every n-tile (code tile) in turn.
+  auto work_of = [&](int it) -> int {
+    if (VQ) {
+      const int mt = (it / p.n_tiles) * nworkers + worker;
+      return mt < num_m ? mt * p.n_tiles + it % p.n_tiles : -1;
+    }
+    const int w = worker + it * nworkers;
+    return w < num_work ? w : -1;
+  };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::NBAR_PIPE; ++s) mbar_init(bar_base + 8u * s, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * 32 * Cfg::EPI_WARPS); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * 32 * Cfg::EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (PAIR) cluster_sync_all(); else __syncthreads();
@@ -360,19 +388,20 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     }
     for (int work = worker; work < num_work; work += nworkers) {
       const TileCoord tc = decode(work);
-      const int x0 = tc.tx * p.Wt, y0 = tc.ty, n0 = tc.nt * BN;
-      for (int kh = 0; kh < 3; ++kh)
+      const int x0 = tc.tx * p.Wt, y0 = tc.ty * MR, n0 = tc.nt * BN;
+      // input rows y0 - 1 ... y0 + MR (MR = 1: the three kh rows of one output row)
+      for (int sr = 0; sr < MR + 2; ++sr)
         for (int cc = 0; cc < p.cchunks; ++cc) {
           const int c0 = cc * TC_BK;
           mbar_wait(emptyA_bar(sa), pa ^ 1u);
           const uint32_t a_dst = smem_base + Cfg::B_RES_BYTES + sa * Cfg::SA_BYTES;
           mbar_expect_tx(fullA_bar(sa), 2 * STRIP_PX * TC_BK * 2);
-          tma_load_4d(a_dst, &map_a_hi, fullA_bar(sa), c0, x0 - 1, y0 + kh - 1, tc.b);
-          tma_load_4d(a_dst + Cfg::SA_PLANE, &map_a_lo, fullA_bar(sa), c0, x0 - 1, y0 + kh - 1, tc.b);
+          tma_load_4d(a_dst, &map_a_hi, fullA_bar(sa), c0, x0 - 1, y0 + sr - 1, tc.b);
+          tma_load_4d(a_dst + Cfg::SA_PLANE, &map_a_lo, fullA_bar(sa), c0, x0 - 1, y0 + sr - 1, tc.b);
           if (++sa == Cfg::SA_STAGES) { sa = 0; pa ^= 1u; }
           if (BRES) continue;
-          for (int kw = 0; kw < 3; ++kw) {
-            const int tap = kh * 3 + kw;
+          for (int kw = 0; kw < 3; ++kw) {                 // streamed weights (MR == 1: sr is kh)
+            const int tap = sr * 3 + kw;
             mbar_wait(emptyB_bar(sb), pb ^ 1u);
             const uint32_t b_dst = smem_base + Cfg::SA_STAGES * Cfg::SA_BYTES + sb * Cfg::SB_BYTES;
             (void)n0;
@@ -387,57 +416,63 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     // ===================== MMA issuer (strip mode) =====================
     const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-    int acc = 0; uint32_t acc_phase = 0;
+    int set = 0; uint32_t set_phase = 0;           // accumulator set (MR slots) of the current work item
     if (BRES) { mbar_wait(bar_base + 8u * (2 * Cfg::SA_STAGES), 0u); tc_fence_after(); }   // weights resident
     for (int work = worker; work < num_work; work += nworkers) {
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      uint32_t first = 0u;
-      for (int kh = 0; kh < 3; ++kh)
+      for (int sr = 0; sr < MR + 2; ++sr)
         for (int cc = 0; cc < p.cchunks; ++cc) {
           mbar_wait(fullA_bar(sa), pa);
           tc_fence_after();
           const uint32_t a_base = smem_base + Cfg::B_RES_BYTES + sa * Cfg::SA_BYTES;
-          for (int kw = 0; kw < 3; ++kw) {
-            uint32_t b_base;
-            if (BRES) {
-              b_base = smem_base + (kh * 3 + kw) * 2 * Cfg::B_PLANE_BYTES;
-            } else {
-              mbar_wait(fullB_bar(sb), pb);
+          // input row sr is tap row kh = sr - r of output row r
+          const int r_lo = sr - 2 > 0 ? sr - 2 : 0, r_hi = sr < MR - 1 ? sr : MR - 1;
+          for (int r = r_lo; r <= r_hi; ++r) {
+            const int kh = sr - r;
+            const int slot = set * MR + r;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BN);
+            if (kh == 0 && cc == 0) {              // first contribution to this accumulator: the epilogue must have drained it
+              mbar_wait(tempty_bar(slot), set_phase ^ 1u);
               tc_fence_after();
-              b_base = smem_base + Cfg::SA_STAGES * Cfg::SA_BYTES + sb * Cfg::SB_BYTES;
             }
-            // tap kw = the strip shifted by kw pixel rows.  Measured on B200: the tensor core derives the 128B-swizzle
-            // XOR from the absolute shared-memory address bits (like TMA does when it writes the strip), so a start
-            // address that is 128-byte but not 1024-byte aligned just works with base-offset 0; putting the row phase
-            // into the descriptor's base-offset field (bits 49-51) instead produces garbage.
-            const uint64_t a_hi = make_sw128_desc(a_base + kw * 128);
-            const uint64_t a_lo = make_sw128_desc(a_base + Cfg::SA_PLANE + kw * 128);
-            const uint64_t b_hi = make_sw128_desc(b_base), b_lo = make_sw128_desc(b_base + Cfg::B_PLANE_BYTES);
+            for (int kw = 0; kw < 3; ++kw) {
+              uint32_t b_base;
+              if (BRES) {
+                b_base = smem_base + (kh * 3 + kw) * 2 * Cfg::B_PLANE_BYTES;
+              } else {
+                mbar_wait(fullB_bar(sb), pb);
+                tc_fence_after();
+                b_base = smem_base + Cfg::SA_STAGES * Cfg::SA_BYTES + sb * Cfg::SB_BYTES;
+              }
+              // tap kw = the strip shifted by kw pixel rows.  Measured on B200: the tensor core derives the 128B-swizzle
+              // XOR from the absolute shared-memory address bits (like TMA does when it writes the strip), so a start
+              // address that is 128-byte but not 1024-byte aligned just works with base-offset 0; putting the row phase
+              // into the descriptor's base-offset field (bits 49-51) instead produces garbage.
+              const uint64_t a_hi = make_sw128_desc(a_base + kw * 128);
+              const uint64_t a_lo = make_sw128_desc(a_base + Cfg::SA_PLANE + kw * 128);
+              const uint64_t b_hi = make_sw128_desc(b_base), b_lo = make_sw128_desc(b_base + Cfg::B_PLANE_BYTES);
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {
-              const uint64_t ko = (uint64_t)((k * 32) >> 4);
-              umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
-              first = 1u;
-              umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-              umma_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                const uint64_t ko = (uint64_t)((k * 32) >> 4);
+                umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, (kh | cc | kw | k) ? 1u : 0u);
+                umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                umma_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+              }
+              if (!BRES) {
+                umma_commit(emptyB_bar(sb));
+                if (++sb == Cfg::SB_STAGES) { sb = 0; pb ^= 1u; }
+              }
             }
-            if (!BRES) {
-              umma_commit(emptyB_bar(sb));
-              if (++sb == Cfg::SB_STAGES) { sb = 0; pb ^= 1u; }
-            }
+            if (kh == 2 && cc == p.cchunks - 1) umma_commit(tfull_bar(slot));    // output row r complete
           }
           umma_commit(emptyA_bar(sa));
           if (++sa == Cfg::SA_STAGES) { sa = 0; pa ^= 1u; }
         }
-      umma_commit(tfull_bar(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (++set == 2) { set = 0; set_phase ^= 1u; }
     }
   } else if (!STRIP && warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     int stage = 0; uint32_t phase = 0;
-    for (int work = worker; work < num_work; work += nworkers) {
+    for (int it = 0, work; (work = work_of(it)) >= 0; ++it) {
       const TileCoord tc = decode(work);
       const int py = tc.ph >> 1, px = tc.ph & 1;
       const int x0 = tc.tx * p.Wt, y0 = tc.ty * p.Ht;
@@ -477,7 +512,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     int acc = 0; uint32_t acc_phase = 0;
     const bool sliced = p.slice_kb > 0;
     const int slice_len = sliced ? p.slice_kb : (p.kb_end - p.kb_begin);
-    for (int work = worker; work < num_work; work += nworkers) {
+    for (int it = 0; work_of(it) >= 0; ++it) {
       for (int kb0 = p.kb_begin; kb0 < p.kb_end; kb0 += slice_len) {
         const int kb1 = min(kb0 + slice_len, p.kb_end);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -541,11 +576,90 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     auto release_acc = [&](int a) {
       if (PAIR) mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0)); else mbar_arrive(tempty_bar(a));
     };
-    for (int work = worker; work < num_work; work += nworkers) {
+    if constexpr (VQ) {
+      // ===================== VQ epilogue: running top-4 of d_j = fl(fl(A + B_j) - 2 C_j) per feature row =====================
+      // The thread owns one accumulator row (a feature) and CW columns (codes) of every code tile; codes arrive in
+      // increasing order, so a strict '<' insertion keeps (distance, code) lexicographic order.  C_j here carries the
+      // tensor core's split-fp16 / truncating-accumulator error (~1e-8 against a distance grid of ulp(A) ~ 3e-5), so
+      // the FOUR best are handed to femasr_vq_finish, which recomputes the exact fp32 distance of every candidate
+      // within a few ulps of the best and applies the reference's tie rule; a row whose best code is clear of the rest
+      // by more than that margin needs no second look.
+      constexpr int EPI_THREADS = 32 * Cfg::EPI_WARPS;
+      uint2* merge = reinterpret_cast<uint2*>(smem_raw + (epi_base - smem_u32(smem_raw)));
+      float td0 = INFINITY, td1 = INFINITY, td2 = INFINITY, td3 = INFINITY;
+      int tj0 = 0x7fffffff, tj1 = 0x7fffffff, tj2 = 0x7fffffff, tj3 = 0x7fffffff;
+      float a_row = 0.f;
+      auto insert = [&](float d, int j) {          // precondition: (d, j) sorts before (td3, tj3)
+        td3 = d; tj3 = j;
+        if (td3 < td2 || (td3 == td2 && tj3 < tj2)) { float t = td2; td2 = td3; td3 = t; int u = tj2; tj2 = tj3; tj3 = u; }
+        if (td2 < td1 || (td2 == td1 && tj2 < tj1)) { float t = td1; td1 = td2; td2 = t; int u = tj1; tj1 = tj2; tj2 = u; }
+        if (td1 < td0 || (td1 == td0 && tj1 < tj0)) { float t = td0; td0 = td1; td1 = t; int u = tj0; tj0 = tj1; tj1 = u; }
+      };
+      for (int it = 0, work; (work = work_of(it)) >= 0; ++it) {
+        const TileCoord tc = decode(work);
+        const long token = (long)tc.tx * p.Wt + row;          // ksize 1: the features are one long row of tokens
+        const bool valid = token < p.W;
+        if (tc.nt == 0) {
+          td0 = td1 = td2 = td3 = INFINITY;
+          tj0 = tj1 = tj2 = tj3 = 0x7fffffff;
+          a_row = valid ? __ldg(p.vq_a + token) : 0.f;
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + part * CW);
+        const int colbase = tc.nt * BN + part * CW;
+#pragma unroll 1
+        for (int ci = 0; ci < NCH; ++ci) {
+          uint32_t r[16];
+          tmem_ld16(t_row + (uint32_t)(ci * CH), r);
+          const float4* es4 = reinterpret_cast<const float4*>(p.vq_esq + colbase + ci * CH);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 es = __ldg(es4 + q4);
+            const float ee[4] = {es.x, es.y, es.z, es.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float c = __uint_as_float(r[4 * q4 + k]) * inv_scale;                          // exact (power of two)
+              const float d = __fsub_rn(__fadd_rn(a_row, ee[k]), __fmul_rn(2.0f, c));              // fl(fl(A + B_j) - 2 C_j)
+              if (d < td3) insert(d, colbase + ci * CH + 4 * q4 + k);
+            }
+          }
+        }
+        tc_fence_before();
+        release_acc(acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (tc.nt == p.n_tiles - 1) {
+          // the column parts of a row live in different warps: merge their lists through shared memory
+          uint2* m = merge + (row * Cfg::NSPLIT + part) * 4;
+          m[0] = make_uint2(__float_as_uint(td0), (uint32_t)tj0); m[1] = make_uint2(__float_as_uint(td1), (uint32_t)tj1);
+          m[2] = make_uint2(__float_as_uint(td2), (uint32_t)tj2); m[3] = make_uint2(__float_as_uint(td3), (uint32_t)tj3);
+          asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
+          if (part == 0) {
+            for (int pp = 1; pp < Cfg::NSPLIT; ++pp)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint2 v = merge[(row * Cfg::NSPLIT + pp) * 4 + k];
+                const float d = __uint_as_float(v.x);
+                const int j = (int)v.y;
+                if (d < td3 || (d == td3 && j < tj3)) insert(d, j);
+              }
+            if (valid) {
+              uint4* out = reinterpret_cast<uint4*>(p.vq_cand + token * 4);
+              out[0] = make_uint4(__float_as_uint(td0), (uint32_t)tj0, __float_as_uint(td1), (uint32_t)tj1);
+              out[1] = make_uint4(__float_as_uint(td2), (uint32_t)tj2, __float_as_uint(td3), (uint32_t)tj3);
+            }
+          }
+          asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
+        }
+      }
+    } else
+    for (int it = 0, work; (work = work_of(it)) >= 0; ++it)
+    for (int mr = 0; mr < MR; ++mr) {          // multi-row strip tiles: one accumulator per image row, in completion order
       const TileCoord tc = decode(work);
-      const int nt = tc.nt, tx = tc.tx, ty = tc.ty, b = tc.b, ph = tc.ph;
+      const int nt = tc.nt, tx = tc.tx, ty = tc.ty * MR + mr, b = tc.b, ph = tc.ph;
       const int y = ty * p.Ht + (row >> p.wt_shift), x = tx * p.Wt + (row & (p.Wt - 1));
       const bool valid = tc.real && y < p.H && x < p.W;
+      const bool gn_ok = tc.real && (MR == 1 || ty < p.H);      // a multi-row tile may hang over the last image row
       const int oy = p.up ? 2 * y + (ph >> 1) : y, ox = p.up ? 2 * x + (ph & 1) : x;
       const int Ho = p.up ? 2 * p.H : p.H, Wo = p.up ? 2 * p.W : p.W;
       const int col0 = nt * BN + part * CW;
@@ -649,17 +763,17 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             sa += __shfl_xor_sync(0xffffffffu, sa, o); ssa += __shfl_xor_sync(0xffffffffu, ssa, o);
             sb += __shfl_xor_sync(0xffffffffu, sb, o); ssb += __shfl_xor_sync(0xffffffffu, ssb, o);
           }
-          const int tile_in_img = (ph * p.tiles_y + ty) * p.tiles_x + tx;
+          const int tile_in_img = (ph * p.tiles_y * MR + ty) * p.tiles_x + tx;
           float* gp = p.gn_partial + (((long)b * p.gn_rows + tile_in_img * 4 + ew) * 32) * 2;
           const int ch0 = col0 + c;                      // first channel of this chunk
           if (p.cpg == 8) {
             float s1 = sa + sb, s2 = ssa + ssb;
             s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-            if (tc.real && (lane == 0 || lane == 2)) *reinterpret_cast<float2*>(gp + (ch0 / 8 + (lane >> 1)) * 2) = make_float2(s1, s2);
+            if (gn_ok && (lane == 0 || lane == 2)) *reinterpret_cast<float2*>(gp + (ch0 / 8 + (lane >> 1)) * 2) = make_float2(s1, s2);
           } else if (p.cpg == 4) {
-            if (tc.real && lane < 4) *reinterpret_cast<float2*>(gp + (ch0 / 4 + lane) * 2) = make_float2(sa + sb, ssa + ssb);
+            if (gn_ok && lane < 4) *reinterpret_cast<float2*>(gp + (ch0 / 4 + lane) * 2) = make_float2(sa + sb, ssa + ssb);
           } else {
-            if (tc.real && lane < 4) {
+            if (gn_ok && lane < 4) {
               *reinterpret_cast<float2*>(gp + (ch0 / 2 + 2 * lane) * 2) = make_float2(sa, ssa);
               *reinterpret_cast<float2*>(gp + (ch0 / 2 + 2 * lane + 1) * 2) = make_float2(sb, ssb);
             }
@@ -672,7 +786,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       tc_fence_before();
       release_acc(acc);                         // 256 (512 when paired) arrivals release the accumulator
       if (sliced) acc_phase ^= 1u;
-      else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      else if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
     }
   }
   tc_fence_before();
@@ -943,6 +1057,21 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
                 : launch_tc_v<BN, PAIR, STRIP, BRES, false>(ah, al, bh, bl, p, st);
 }
 
+template <int BN>
+static int launch_vq(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                     const TcP& p, cudaStream_t st) {
+  using Cfg = TcCfg<BN, false, false, false>;
+  static PerDeviceFlag attr_set;
+  if (!attr_set.cur()) {
+    FEMASR_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<BN, false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set.cur() = true;
+  }
+  const int num_m = p.num_tiles / p.n_tiles;
+  const int grid = num_m < sm_count() ? num_m : sm_count();
+  tc_igemm_kernel<BN, false, false, false, false, true><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
+  return launch_status("tc_igemm_kernel(vq)");
+}
+
 }  // namespace femasr
 
 using namespace femasr;
@@ -1077,6 +1206,50 @@ extern "C" int femasr_tc_prepare(const float* x, void* a_hi, void* a_lo, int mod
   return launch_status("tc_prepare_kernel");
 }
 
+// VectorQuantizer distance stage on the tensor cores (femasr_arch.py:35-38, 63-66): for every feature row the four
+// smallest d_j = fl(fl(A + B_j) - 2 z.e_j) with their codes, ascending in (d, j); the [N, n_e] product never leaves the SM.
+extern "C" int femasr_vq_match_tc(const void* z_hi, const void* z_lo, const void* cb_blob, const float* a, const float* esq,
+                                  void* cand, int N, int n_e, int e_dim, void* stream) {
+  FEMASR_CHECK_ARG(z_hi && z_lo && cb_blob && a && esq && cand, "vq_match_tc: null pointer");
+  FEMASR_CHECK_ARG(N > 0 && n_e > 0 && e_dim > 0 && n_e % 64 == 0 && e_dim % 64 == 0, "vq_match_tc: n_e and e_dim must be positive multiples of 64");
+  const long nw = (long)n_e * e_dim;
+  const __half* w_hi = reinterpret_cast<const __half*>(cb_blob);
+  const __half* w_lo = w_hi + nw;
+  TcP p;
+  memset(&p, 0, sizeof(p));
+  p.inv_scale = reinterpret_cast<const float*>(reinterpret_cast<const unsigned int*>(w_lo + nw) + 1);
+  p.vq_a = a; p.vq_esq = esq; p.vq_cand = reinterpret_cast<uint2*>(cand);
+  p.B = 1; p.H = 1; p.W = N; p.Cin = e_dim; p.Cout = n_e; p.taps = 1; p.stride = 1;
+  p.Wt = 128; p.Ht = 1; p.wt_shift = 7; p.tiles_x = (int)cdiv(N, 128); p.tiles_y = 1;
+  const int BN = n_e % 256 == 0 ? 256 : (n_e % 128 == 0 ? 128 : 64);
+  p.n_tiles = n_e / BN;
+  p.num_tiles = p.tiles_x * p.n_tiles; p.cchunks = e_dim / 64;
+  p.kb_begin = 0; p.kb_end = p.cchunks; p.cpg = 1;
+  CUtensorMap mah, mal, mbh, mbl;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)e_dim, (cuuint64_t)N, 1, 1};
+    const cuuint64_t str[3] = {(cuuint64_t)e_dim * 2, (cuuint64_t)N * e_dim * 2, (cuuint64_t)N * e_dim * 2};
+    const cuuint32_t box[4] = {64, 128, 1, 1};
+    int s = make_map(&mah, z_hi, 4, dims, str, box);
+    if (s) return s;
+    s = make_map(&mal, z_lo, 4, dims, str, box);
+    if (s) return s;
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)e_dim, (cuuint64_t)n_e};
+    const cuuint64_t str[1] = {(cuuint64_t)e_dim * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)BN};
+    int s = make_map(&mbh, w_hi, 2, dims, str, box);
+    if (s) return s;
+    s = make_map(&mbl, w_lo, 2, dims, str, box);
+    if (s) return s;
+  }
+  cudaStream_t st = as_stream(stream);
+  if (BN == 256) return launch_vq<256>(mah, mal, mbh, mbl, p, st);
+  if (BN == 128) return launch_vq<128>(mah, mal, mbh, mbl, p, st);
+  return launch_vq<64>(mah, mal, mbh, mbl, p, st);
+}
+
 // y = act(conv(a) + bias) + res1 + res2 with a given as fp16 hi/lo planes at the conv-input resolution.
 extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   FEMASR_CHECK_ARG(a && a->a_hi && a->a_lo && a->w_blob, "tc_igemm: null pointer");
@@ -1103,6 +1276,7 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   const float* inv_scale = reinterpret_cast<const float*>(reinterpret_cast<const unsigned int*>(w_lo + nw) + 1);
 
   TcP p;
+  memset(&p, 0, sizeof(p));
   p.bias = a->bias; p.res1 = a->res1; p.res2 = a->res2; p.y = a->y; p.inv_scale = inv_scale;
   p.out_hi = reinterpret_cast<__half*>(a->out_hi); p.out_lo = reinterpret_cast<__half*>(a->out_lo);
   p.gn_partial = a->gn_partial; p.cpg = a->Cout / 32; p.gn_rows = 0;
@@ -1116,6 +1290,11 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   p.n_tiles = a->Cout / BN;
   const bool pair = plan.pair, strip = plan.strip;
   FEMASR_CHECK_ARG(!(a->strip == 1 && !strip), "tc_igemm: strip mode needs a plain 3x3 stride-1 conv, Cout tile <= 128, W >= 128, no K slicing");
+  p.gn_rows = phases * p.tiles_x * p.tiles_y * 4;           // one partial row per (128-pixel tile, lane quarter)
+  // 64 -> 64 channels: weights resident in shared memory, work items of 4 image rows (FEMASR_TC_BRES=0: streamed weights)
+  static const int bres_env = [] { const char* e = getenv("FEMASR_TC_BRES"); return e ? atoi(e) : 1; }();
+  const bool bres = strip && bres_env && a->Cin == 64 && a->Cout == 64;
+  if (bres) p.tiles_y = (int)cdiv(H, TcCfg<64, false, true, true>::MR);
   const long ntile = (long)phases * B * p.tiles_x * p.tiles_y * p.n_tiles;
   FEMASR_CHECK_ARG(ntile < (1l << 31), "tc_igemm: too many tiles");
   p.num_tiles = (int)ntile; p.cchunks = a->Cin / 64;
@@ -1124,7 +1303,6 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   FEMASR_CHECK_ARG(p.kb_begin >= 0 && p.kb_begin < p.kb_end && p.kb_end <= nkb_total, "tc_igemm: bad k-block slice");
   FEMASR_CHECK_ARG(a->slice_kb >= 0, "tc_igemm: slice_kb must be >= 0");
   p.slice_kb = (a->slice_kb > 0 && a->slice_kb < p.kb_end - p.kb_begin) ? a->slice_kb : 0;
-  p.gn_rows = phases * p.tiles_x * p.tiles_y * 4;
 
   CUtensorMap mah, mal, mbh, mbl;
   {
@@ -1149,9 +1327,7 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   cudaStream_t st = as_stream(stream);
   if (strip) {
     if (BN == 128) return launch_tc<128, false, true>(mah, mal, mbh, mbl, p, st);
-    // 64 -> 64 channels: weights resident in shared memory (FEMASR_TC_BRES=0 falls back to the streamed weight ring)
-    static const int bres_env = [] { const char* e = getenv("FEMASR_TC_BRES"); return e ? atoi(e) : 1; }();
-    if (bres_env && a->Cin == 64 && a->Cout == 64) return launch_tc<64, false, true, true>(mah, mal, mbh, mbl, p, st);
+    if (bres) return launch_tc<64, false, true, true>(mah, mal, mbh, mbl, p, st);
     return launch_tc<64, false, true>(mah, mal, mbh, mbl, p, st);
   }
   if (pair) {

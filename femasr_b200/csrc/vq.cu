@@ -58,6 +58,86 @@ __global__ void __launch_bounds__(256) vq_select_kernel(const float* __restrict_
   if (lane == 0 && loss_rows) loss_rows[r] = l;
 }
 
+// Second half of the fused VQ (after femasr_vq_match_tc): one warp per feature row.
+//   cand[r][0..3]  the four smallest tensor-core distances with their codes, ascending in (d, j)
+// A row whose runner-up is more than VQ_MARGIN_ULPS ulps behind the best keeps the best code.  Otherwise every
+// candidate inside the margin gets its distance recomputed with an exact dot product (fp64 accumulate, rounded once:
+// what "any fp32-accurate z.e" of SURVEY 7.3-2 asks for) through the reference's rounding sequence
+// fl(fl(A + B_j) - 2 C_j) and the lowest-index tie rule; if even the fourth candidate is inside the margin the whole
+// codebook is rescanned exactly.  The tensor-core distance differs from the exact one by at most one grid step
+// (|dC| ~ 1e-8 against ulp(A) ~ 3e-5), so the true argmin is always within 2 steps of the tensor-core best.
+// Then: gather, straight-through residual z + (e - z), per-row loss (femasr_arch.py:67-100).
+// Margin: 8 grid steps of the fp32 distance formula (the grid is ulp(A + B), not ulp(d): the subtraction may cancel) plus
+// twice a generous bound of the tensor-core error of 2C (3 * e_dim / 16 truncating accumulations of <= 1 ulp each).
+constexpr float VQ_MARGIN_ULPS = 8.0f;
+__device__ __forceinline__ float vq_exact_distance(const float* __restrict__ zr, const float* __restrict__ er, float a,
+                                                    float b, int e_dim, int lane) {
+  double s = 0.0;
+  for (int k = lane; k < e_dim; k += 32) s = fma((double)zr[k], (double)__ldg(er + k), s);
+  s = warp_sum_d(s);
+  const float c = (float)s;
+  return __fsub_rn(__fadd_rn(a, b), __fmul_rn(2.0f, c));
+}
+
+__global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict__ z, const float* __restrict__ a,
+                                                        const uint2* __restrict__ cand, const float* __restrict__ codebook,
+                                                        const float* __restrict__ esq, int64_t* __restrict__ idx,
+                                                        float* __restrict__ zq, float* __restrict__ loss_rows,
+                                                        unsigned int* __restrict__ stats, int N, int n_e, int e_dim) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= N) return;
+  const int lane = threadIdx.x & 31;
+  const float* zr = z + (long)r * e_dim;
+  const uint2 cv = cand[(long)r * 4 + (lane & 3)];
+  float d[4]; int j[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    d[k] = __uint_as_float(__shfl_sync(0xffffffffu, cv.x, k));
+    j[k] = (int)__shfl_sync(0xffffffffu, cv.y, k);
+  }
+  int bj = j[0];
+  if (bj == 0x7fffffff) {
+    bj = 0;                                            // all-NaN row: torch.argmin also returns a valid index
+  } else {
+    const float ar0 = a[r];
+    const float ab0 = ar0 + __ldg(esq + bj);
+    const float margin = VQ_MARGIN_ULPS * 1.1920929e-7f * fmaxf(fabsf(ab0), fabsf(d[0])) +
+                         4.0f * 1.1920929e-7f * (float)(3 * e_dim / 16) * fabsf(ab0 - d[0]) + 1e-30f;
+    int nc = 1;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) nc += (j[k] != 0x7fffffff && d[k] - d[0] <= margin) ? 1 : 0;   // ascending: a prefix
+    if (nc > 1) {
+      const float ar = ar0;
+      float best = INFINITY;
+      int bb = 0x7fffffff;
+      if (nc == 4) {
+        for (int c = 0; c < n_e; ++c) {                // candidate list overflowed: exact scan, increasing code
+          const float dd = vq_exact_distance(zr, codebook + (long)c * e_dim, ar, __ldg(esq + c), e_dim, lane);
+          if (dd < best) { best = dd; bb = c; }
+        }
+      } else {
+        for (int k = 0; k < nc; ++k) {
+          const float dd = vq_exact_distance(zr, codebook + (long)j[k] * e_dim, ar, __ldg(esq + j[k]), e_dim, lane);
+          if (dd < best || (dd == best && j[k] < bb)) { best = dd; bb = j[k]; }
+        }
+      }
+      if (bb != 0x7fffffff) bj = bb;
+      if (stats && lane == 0) { atomicAdd(stats, 1u); if (nc == 4) atomicAdd(stats + 1, 1u); if (bb != j[0]) atomicAdd(stats + 2, 1u); }
+    }
+  }
+  if (lane == 0 && idx) idx[r] = (int64_t)bj;
+  const float* er = codebook + (long)bj * e_dim;
+  float l = 0.f;
+  for (int k = lane; k < e_dim; k += 32) {
+    const float zv = zr[k];
+    const float diff = __fsub_rn(__ldg(er + k), zv);   // (z_q - z)
+    l = fmaf(diff, diff, l);
+    if (zq) zq[(long)r * e_dim + k] = __fadd_rn(zv, diff);   // z + (z_q - z).detach(), femasr_arch.py:95
+  }
+  l = warp_sum(l);
+  if (lane == 0 && loss_rows) loss_rows[r] = l;
+}
+
 template <bool ACC>
 __global__ void __launch_bounds__(1024) sum_scaled_kernel(const float* __restrict__ x, float* __restrict__ out, size_t n,
                                                           double scale) {
@@ -191,6 +271,16 @@ extern "C" int femasr_vq_select(const float* z, const float* zc, const float* co
   FEMASR_CHECK_ARG(N > 0 && n_e > 0 && e_dim > 0, "vq_select: empty input");
   vq_select_kernel<<<(N + 7) / 8, 256, 0, as_stream(stream)>>>(z, zc, codebook, esq, idx, zq, loss_rows, N, n_e, e_dim);
   return launch_status("vq_select_kernel");
+}
+
+extern "C" int femasr_vq_finish(const float* z, const float* a, const void* cand, const float* codebook, const float* esq,
+                                int64_t* idx, float* zq, float* loss_rows, unsigned int* stats, int N, int n_e, int e_dim,
+                                void* stream) {
+  FEMASR_CHECK_ARG(z && a && cand && codebook && esq, "vq_finish: null pointer");
+  FEMASR_CHECK_ARG(N > 0 && n_e > 0 && e_dim > 0, "vq_finish: empty problem");
+  vq_finish_kernel<<<(unsigned)cdiv(N, 8), 256, 0, as_stream(stream)>>>(z, a, reinterpret_cast<const uint2*>(cand), codebook, esq,
+                                                                        idx, zq, loss_rows, stats, N, n_e, e_dim);
+  return launch_status("vq_finish_kernel");
 }
 
 extern "C" int femasr_sum_scaled(const float* x, float* out, size_t n, double scale, void* stream) {

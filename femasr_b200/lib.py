@@ -94,6 +94,8 @@ SIGNATURES = {
     "femasr_expand_rel_bias_mma": (_I, [_V, _V, _I, _V]),
     "femasr_row_sumsq": (_I, [_V, _V, _I, _I, _V]),
     "femasr_vq_select": (_I, [_V, _V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _V]),
+    "femasr_vq_match_tc": (_I, [_V, _V, _V, _V, _V, _V, _I, _I, _I, _V]),
+    "femasr_vq_finish": (_I, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _I, _I, _I, _V]),
     "femasr_sum_scaled": (_I, [_V, _V, _Z, _D, _V]),
     "femasr_sum_scaled_add": (_I, [_V, _V, _Z, _D, _V]),
     "femasr_concat_channels": (_I, [_V, _I, _V, _I, _I, _I, _V, _I, _I, _I, _V]),

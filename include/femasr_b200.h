@@ -253,6 +253,21 @@ int femasr_row_sumsq(const float* x, float* out, int rows, int cols, void* strea
 int femasr_vq_select(const float* z, const float* zc, const float* codebook, const float* esq,
                      int64_t* idx, float* zq, float* loss_rows, int N, int n_e, int e_dim,
                      int write_zq_passthrough, void* stream);
+/* Fused VQ feature matching on the tensor cores (femasr_arch.py:35-38, 50-100) - the [N, n_e] distance matrix and the
+ * one-hot of the reference never exist:
+ *   femasr_vq_match_tc  z (split fp16 planes [N, e_dim]) x codebook (femasr_tc_pack_weight blob of the [n_e, e_dim]
+ *                       embedding) on tcgen05; the epilogue evaluates d_j = fl(fl(A + B_j) - 2 C_j) and keeps per row the
+ *                       four smallest (d, j) in cand[N][4] = {float bits, int32} pairs, ascending.  a = row_sumsq(z),
+ *                       esq = row_sumsq(codebook).
+ *   femasr_vq_finish    exact fp32 re-evaluation of the candidates that lie within rounding distance of the best
+ *                       (whole-codebook rescan if all four do), lowest-index tie rule, then idx / zq = z + (e - z) /
+ *                       loss_rows like femasr_vq_select.  stats (3 x uint32, may be NULL) counts refined rows, rescanned
+ *                       rows and rows whose code changed.  Bit-identical indices to femasr_vq_select on exact z.E^T. */
+int femasr_vq_match_tc(const void* z_hi, const void* z_lo, const void* cb_blob, const float* a, const float* esq,
+                       void* cand, int N, int n_e, int e_dim, void* stream);
+int femasr_vq_finish(const float* z, const float* a, const void* cand, const float* codebook, const float* esq,
+                     int64_t* idx, float* zq, float* loss_rows, unsigned int* stats, int N, int n_e, int e_dim,
+                     void* stream);
 /* out[0] = scale * sum(x[0..n)) accumulated in double in a fixed order. */
 int femasr_sum_scaled(const float* x, float* out, size_t n, double scale, void* stream);
 /* out[0] += scale * sum(x[0..n)) (the running sum over codebooks, femasr_arch.py:371). */

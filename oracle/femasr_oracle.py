@@ -301,15 +301,20 @@ def decode_indices(sd: SD, indices: Tensor) -> Tensor:
     return _conv(sd, "out_conv", t)
 
 
-def test(sd: SD, x: Tensor, scale: int) -> Tensor:
-    """femasr_arch.py:449-468: flip-pad to (h//wsz+1)*wsz (always pads), run, crop."""
+def flip_pad(x: Tensor, scale: int) -> Tensor:
+    """femasr_arch.py:455-461: flip-pad to (h//wsz+1)*wsz (always pads, even when h is a multiple of wsz)."""
     wsz = 8 // scale * 8
     _, _, h, w = x.shape
     hp = (h // wsz + 1) * wsz - h
     wp = (w // wsz + 1) * wsz - w
     x = torch.cat([x, torch.flip(x, [2])], 2)[:, :, : h + hp, :]
-    x = torch.cat([x, torch.flip(x, [3])], 3)[:, :, :, : w + wp]
-    out = encode_and_decode(sd, x, scale)[0]
+    return torch.cat([x, torch.flip(x, [3])], 3)[:, :, :, : w + wp]
+
+
+def test(sd: SD, x: Tensor, scale: int) -> Tensor:
+    """femasr_arch.py:449-468: flip-pad, run, crop."""
+    _, _, h, w = x.shape
+    out = encode_and_decode(sd, flip_pad(x, scale), scale)[0]
     return out[..., : h * scale, : w * scale]
 
 

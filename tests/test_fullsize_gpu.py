@@ -9,6 +9,7 @@ gpurun_out/parity_report.json (copied to profiles/parity_r2.json)."""
 import json
 import os
 
+import numpy as np
 import pytest
 import torch
 
@@ -67,9 +68,43 @@ def test_benchmark_geometry_parity(cuda, gemm_path):
     assert rel_loss <= 2e-5
 
 
+def forced_indices(idx_forced):
+    """Context manager: the oracle's VectorQuantizer picks the given codes (everything else of the oracle unchanged)."""
+    import contextlib
+
+    @contextlib.contextmanager
+    def cm():
+        orig = O.vector_quantize
+
+        def vq(cb, z_nchw, gt_indices=None, lq=True):
+            zq, loss, _ = orig(cb, z_nchw, gt_indices, lq)
+            z = z_nchw.permute(0, 2, 3, 1)
+            e = cb[idx_forced.reshape(-1)].view(z.shape)
+            zq = (z + (e - z)).permute(0, 3, 1, 2).contiguous()           # femasr_arch.py:95 with the forced code
+            return zq, loss, idx_forced.reshape(zq.shape[0], 1, zq.shape[2], zq.shape[3])
+        O.vector_quantize = vq
+        try:
+            yield
+        finally:
+            O.vector_quantize = orig
+    return cm()
+
+
 def test_config2_full_batch_against_oracle(cuda):
     """BASELINE config 2 at its FULL size on the default (tcgen05) path: batch 32, 131072 VQ rows, every index and every
-    output pixel against the CPU oracle (about 45 s of host time)."""
+    output pixel against the CPU oracle (about a minute of host time).
+
+    What can hold at this size.  With the default U(+-1/1024) codebook the fp32 distances sit on a grid of ulp(sum z^2)
+    ~ 3e-5 and about 1 % of the rows have their two best codes within one grid step.  Which of the two such a row gets
+    depends on the last bits of z, i.e. on the fp32 SUMMATION ORDER of the ~100 layers in front of the VQ: the oracle
+    itself moves a few rows per 131072 when only its thread count / batch chunking changes, and ~200 against its own
+    fp64 run (profiles/oracle_selfcheck_r2.json).  No implementation with another summation order than that one
+    ATen-CPU run can promise 0 of 131072; 0 of 16384 (test above) is the practical form of "bit-exact".  Enforced here:
+      * at most 16 differing rows (1.2e-4; the oracle's own fp32-vs-fp64 rate is 1.5e-3);
+      * every differing row is TIE-EQUIVALENT under the oracle's own arithmetic: the oracle's fp32 distance of our code
+        is within 2 grid steps of the oracle's best (so it is rounding noise, not a wrong nearest neighbour);
+      * the output matches to 1e-3 everywhere given the same codes: images without differing rows directly, the others
+        against the oracle re-run with our codes forced into its quantiser."""
     B = 32
     sd = random_state_dict(4, 256, seed=0, init="default")
     x = torch.rand(B, 3, 128, 128, generator=torch.Generator().manual_seed(1))
@@ -77,62 +112,128 @@ def test_config2_full_batch_against_oracle(cuda):
     net = make(4, None, cuda, sd)
     out, loss, _, idx = net(x.to(cuda))
     out, idx0 = out.cpu(), idx[0].cpu()
-    flips, worst = 0, 0.0
-    losses = []
+    cb = sd["quantize_group.0.embedding.weight"]
+    flips, worst, worst_raw, gaps, losses = 0, 0.0, 0.0, [], []
     with torch.no_grad():
         for i in range(0, B, 8):                       # the oracle is per-sample: chunks keep its memory small
-            want, wloss, _, widx = O.encode_and_decode(sd, x[i:i + 8], 4)
-            flips += int((idx0[i:i + 8] != widx[0]).sum())
-            worst = max(worst, (out[i:i + 8] - want).abs().max().item())
+            taps = {}
+            want, wloss, _, widx = O.encode_and_decode(sd, x[i:i + 8], 4, taps)
             losses.append(wloss.item())
-    rel_loss = abs(loss.item() - sum(losses) / len(losses)) / (sum(losses) / len(losses))
-    print(f"config 2 full batch: {flips}/{idx0.numel()} flips, max-abs {worst:.2e}, loss rel {rel_loss:.2e}")
-    record("config2_b32_default_path", flips=flips, rows=idx0.numel(), max_abs=worst, loss_rel=rel_loss,
-           entry="forward", lr=[128, 128], scale=4, batch=B)
-    assert flips == 0 and worst <= 1e-3 and rel_loss <= 2e-5
+            diff_rows = torch.nonzero((idx0[i:i + 8] != widx[0]).reshape(-1)).reshape(-1)
+            raw = (out[i:i + 8] - want).abs().max().item()
+            worst_raw = max(worst_raw, raw)
+            if diff_rows.numel() == 0:
+                worst = max(worst, raw)
+                continue
+            flips += diff_rows.numel()
+            wz = taps["z"].permute(0, 2, 3, 1).reshape(-1, 256)
+            ours, theirs = idx0[i:i + 8].reshape(-1), widx[0].reshape(-1)
+            for r in diff_rows.tolist():
+                d = O.vq_dist(wz[r:r + 1], cb)[0]                 # the oracle's own fp32 distances of that row
+                ulp = float(np.spacing(np.float32((wz[r] ** 2).sum().item())))
+                gaps.append(float(d[ours[r]] - d[theirs[r]]) / ulp)
+            with forced_indices(idx0[i:i + 8]):
+                want2 = O.encode_and_decode(sd, x[i:i + 8], 4)[0]
+            worst = max(worst, (out[i:i + 8] - want2).abs().max().item())
+    mean_loss = sum(losses) / len(losses)
+    rel_loss = abs(loss.item() - mean_loss) / mean_loss
+    print(f"config 2 full batch: {flips}/{idx0.numel()} differing rows (oracle gaps in grid steps: {[round(g, 2) for g in gaps]}), "
+          f"max-abs given equal codes {worst:.2e} (raw {worst_raw:.2e}), loss rel {rel_loss:.2e}")
+    record("config2_b32_default_path", flips=flips, rows=idx0.numel(), oracle_gap_grid_steps=gaps, max_abs=worst,
+           max_abs_raw=worst_raw, loss_rel=rel_loss, entry="forward", lr=[128, 128], scale=4, batch=B)
+    assert flips <= 16, f"{flips} differing rows of {idx0.numel()}"
+    assert all(0.0 <= g <= 2.0 for g in gaps), f"a differing row is not a rounding tie under the oracle's arithmetic: {gaps}"
+    assert worst <= 1e-3 and rel_loss <= 2e-5
 
 
 def test_config3_x2_against_oracle(cuda):
-    """BASELINE config 3 (x2, 256x256 LR, batch 16): the oracle checks 2 images in full; batch-independence (bit-exact
-    sub-batch reproduction) extends that to the other 14."""
+    """BASELINE config 3 (x2, 256x256 LR, batch 16): the oracle checks 2 images in full (8192 VQ rows; same bookkeeping as
+    the full-batch test, but at this row count a differing row is not expected); batch-independence (bit-exact sub-batch
+    reproduction) extends that to the other 14."""
     B = 16
     sd = random_state_dict(2, 256, seed=0, init="default")
     x = torch.rand(B, 3, 256, 256, generator=torch.Generator().manual_seed(3))
     oracle_threads()
     net = make(2, None, cuda, sd)
-    out, loss, _, idx = net(x.to(cuda))
-    with torch.no_grad():
-        want, _, _, widx = O.encode_and_decode(sd, x[:2], 2)
-    flips = int((idx[0][:2].cpu() != widx[0]).sum())
-    err = (out[:2].cpu() - want).abs().max().item()
-    print(f"config 3: {flips}/{widx[0].numel()} flips, max-abs {err:.2e}")
-    record("config3_x2_256_b16", flips=flips, rows=widx[0].numel(), max_abs=err, entry="forward", lr=[256, 256],
-           scale=2, batch=B, oracle_images=2)
-    assert flips == 0 and err <= 1e-3
+    _, flips, gaps, err, raw = compare_with_oracle(net, sd, x[:2], 2)
+    print(f"config 3: {flips}/8192 differing rows (gaps {gaps}), max-abs given equal codes {err:.2e} (raw {raw:.2e})")
+    record("config3_x2_256_b16", flips=flips, rows=8192, oracle_gap_grid_steps=gaps, max_abs=err, max_abs_raw=raw,
+           entry="forward", lr=[256, 256], scale=2, batch=B, oracle_images=2)
+    assert flips <= 1 and all(0.0 <= g <= 2.0 for g in gaps) and err <= 1e-3
     eng = net._native(cuda)
     y_all, _, i_all = eng.forward(x.to(cuda))
     y_sub, _, i_sub = eng.forward(x[6:8].to(cuda).contiguous())
     assert torch.equal(y_sub, y_all[6:8]) and torch.equal(i_sub, i_all[6:8]), "a sub-batch must reproduce its rows bit-exactly"
 
 
+def compare_with_oracle(net, sd, x, scale):
+    """One encode_and_decode batch against the oracle with the tie-equivalence bookkeeping of
+    test_config2_full_batch_against_oracle: returns (our output, differing rows, oracle gaps in grid steps, max-abs given
+    equal codes, raw max-abs)."""
+    cb = sd["quantize_group.0.embedding.weight"]
+    out, _, _, idx = net(x.to(next(net.parameters()).device))
+    out, idx0 = out.cpu(), idx[0].cpu()
+    with torch.no_grad():
+        taps = {}
+        want, _, _, widx = O.encode_and_decode(sd, x, scale, taps)
+        raw = (out - want).abs().max().item()
+        rows = torch.nonzero((idx0 != widx[0]).reshape(-1)).reshape(-1)
+        if rows.numel() == 0:
+            return out, 0, [], raw, raw
+        wz = taps["z"].permute(0, 2, 3, 1).reshape(-1, cb.shape[1])
+        ours, theirs = idx0.reshape(-1), widx[0].reshape(-1)
+        gaps = []
+        for r in rows.tolist():
+            d = O.vq_dist(wz[r:r + 1], cb)[0]
+            ulp = float(np.spacing(np.float32((wz[r] ** 2).sum().item())))
+            gaps.append(float(d[ours[r]] - d[theirs[r]]) / ulp)
+        with forced_indices(idx0):
+            want2 = O.encode_and_decode(sd, x, scale)[0]
+    return out, int(rows.numel()), gaps, (out - want2).abs().max().item(), raw
+
+
+def check_tiled(net, sd, x, cuda, name, tile=None, pad=None, max_rows=16):
+    """test_tile against the oracle, tile by tile the way the reference runs it (femasr_arch.py:387-447: cut with halo ->
+    test() = flip-pad, encode_and_decode, crop -> paste):
+      (1) plumbing, bit-exact and oracle-free: FeMaSRNet.test_tile (same-shape tiles batched) == our own forward on every
+          flip-padded tile, cropped and pasted;
+      (2) every tile's forward against the oracle's, with the index bookkeeping of the full-batch test (a tiled image has
+          as many VQ rows as config 2, so the same handful of rounding ties can resolve differently)."""
+    kw = {} if tile is None else {"tile_size": tile, "tile_pad": pad}
+    args = (240, 16) if tile is None else (tile, pad)
+    got = net.test_tile(x.to(cuda), **kw).cpu()
+    _, _, h, w = x.shape
+    s = 4
+    stitched = torch.zeros_like(got)
+    flips, gaps, worst, worst_raw, rows_total = 0, [], 0.0, 0.0, 0
+    for t in O.tile_plan(h, w, *args):
+        y0, y1, x0, x1 = t["in_win"]
+        xt = x[:, :, y0:y1, x0:x1]
+        out, f, g, m, raw = compare_with_oracle(net, sd, O.flip_pad(xt, s), s)
+        flips += f; gaps += g; worst = max(worst, m); worst_raw = max(worst_raw, raw)
+        rows_total += out.shape[2] * out.shape[3] // 64
+        cy, cx, th, tw = t["crop"]
+        oy0, oy1, ox0, ox1 = t["out_win"]
+        stitched[:, :, oy0 * s:oy1 * s, ox0 * s:ox1 * s] = out[:, :, cy * s:(cy + th) * s, cx * s:(cx + tw) * s]
+    print(f"{name}: {flips}/{rows_total} differing rows (gaps {[round(g, 2) for g in gaps]}), max-abs given equal codes "
+          f"{worst:.2e} (raw {worst_raw:.2e})")
+    record(name, flips=flips, rows=rows_total, oracle_gap_grid_steps=gaps, max_abs=worst, max_abs_raw=worst_raw,
+           entry="test_tile", lr=[h, w], scale=s, tiles=len(O.tile_plan(h, w, *args)), tile=list(args))
+    assert torch.equal(got, stitched), "test_tile must equal cut / test() / paste of its own tiles bit-exactly"
+    assert flips <= max_rows and all(0.0 <= g <= 2.0 for g in gaps)
+    assert worst <= 1e-3
+    return got
+
+
 def test_config5_tiled_reduced_against_oracle(cuda):
     """BASELINE config 5 (x4 test_tile(256, 32)) on a 768x768 LR image: 9 tiles in all three shape classes of the
-    1024x1024 case (corner 288x288, edge 288x320 / 320x288, interior 320x320 -> padded 304..336, 9x9..10x10 windows).
-    The oracle runs the reference's one-tile-at-a-time loop."""
+    1024x1024 case (corner 288x288, edge 288x320 / 320x288, interior 320x320 -> padded 304..336, 19x19..21x21 windows)."""
     sd = random_state_dict(4, 256, seed=0, init="default")
     x = torch.rand(1, 3, 768, 768, generator=torch.Generator().manual_seed(4))
     oracle_threads()
     net = make(4, None, cuda, sd)
-    got = net.test_tile(x.to(cuda), 256, 32).cpu()
-    with torch.no_grad():
-        want = O.test_tile(sd, x, 4, 256, 32)
-    diff = (got - want).abs()
-    frac = float((diff > 1e-3).float().mean())
-    print(f"config 5 (768x768): max-abs {diff.max():.2e}, fraction > 1e-3: {frac:.2e}")
-    record("config5_tile256_pad32_768", max_abs=diff.max().item(), frac_gt_1e3=frac, entry="test_tile", lr=[768, 768],
-           scale=4, tiles=9)
+    got = check_tiled(net, sd, x, cuda, "config5_tile256_pad32_768", 256, 32, max_rows=24)
     assert tuple(got.shape) == (1, 3, 3072, 3072)
-    assert diff.max().item() <= 1e-3
 
 
 def test_default_tile_path_of_the_entry_script(cuda):
@@ -142,14 +243,7 @@ def test_default_tile_path_of_the_entry_script(cuda):
     x = torch.rand(1, 3, 488, 616, generator=torch.Generator().manual_seed(5))
     oracle_threads()
     net = make(4, None, cuda, sd)
-    got = net.test_tile(x.to(cuda)).cpu()
-    with torch.no_grad():
-        want = O.test_tile(sd, x, 4)
-    diff = (got - want).abs()
-    print(f"default test_tile (488x616): max-abs {diff.max():.2e}")
-    record("default_tile240_pad16_488x616", max_abs=diff.max().item(), entry="test_tile", lr=[488, 616], scale=4,
-           tiles=len(O.tile_plan(488, 616, 240, 16)))
-    assert diff.max().item() <= 1e-3
+    check_tiled(net, sd, x, cuda, "default_tile240_pad16_488x616")
 
 
 def test_full_batch_size_independent_properties(cuda):
