@@ -109,6 +109,7 @@ struct femasr_net {
   bool profile = false;
   bool tc_precise = true;                 // K-sliced fp32 accumulation for the layers in front of the VQ
   bool oc_mma = true;                     // out_conv on mma.sync in the tensor-core path (FEMASR_OUTCONV_MMA=0: SIMT kernel)
+  bool in_conv_tc = true;                 // in_conv as an im2col GEMM on the tensor cores (FEMASR_IN_CONV_TC=0: fp32 SIMT kernel)
   int tc_slice_kb = 4;                    // K-slice length in 64-wide k-blocks (FEMASR_TC_SLICE_KB; study knob)
   bool vq_fused = true;                   // VQ distances on the tensor cores with the argmin fused (FEMASR_VQ_FUSED=0: fp32 SIMT z.E^T + vq_select)
   bool fast_silu = true;                  // approximate-unit SiLU in the operand staging behind the VQ (FEMASR_FAST_SILU=0: exact)
@@ -640,7 +641,25 @@ struct Ctx {
       in_hi = ar.alloc((in_elems + 1) / 2);
       in_lo = ar.alloc((in_elems + 1) / 2);
       const int c0 = c;
-      run("in_conv", in_flops, [&] { return femasr_in_conv4x4_split(x_nchw, iw, ib, in_hi, in_lo, B, cfg.in_channel, H, W, c0, st); });
+      const std::string wkey = enc + ".in_conv.weight#im2col";
+      if (net->in_conv_tc && (dry() || net->tcw.count(wkey))) {
+        // K = 48 (-> 64) GEMM over im2col rows on the tensor cores, writing the down conv's split planes
+        const size_t rows = (size_t)B * h * w;
+        float* ic_hi = ar.alloc(rows * 64 / 2);
+        float* ic_lo = ar.alloc(rows * 64 / 2);
+        run("in_conv_im2col", 0.0, [&] { return femasr_in_conv_im2col(x_nchw, ic_hi, ic_lo, B, cfg.in_channel, H, W, st); });
+        if (!dry() && ok()) {
+          femasr_tc_args t;
+          memset(&t, 0, sizeof(t));
+          t.a_hi = ic_hi; t.a_lo = ic_lo; t.w_blob = net->tcw[wkey].p; t.bias = ib;
+          t.out_hi = in_hi; t.out_lo = in_lo;
+          t.B = B; t.H = h; t.W = w; t.Cin = 64; t.Cout = c0; t.ksize = 1; t.stride = 1; t.pair = -1; t.strip = -1;
+          run("in_conv", in_flops, [&] { return femasr_tc_igemm(&t, st); });
+        }
+        ar.release(ic_lo); ar.release(ic_hi);
+      } else {
+        run("in_conv", in_flops, [&] { return femasr_in_conv4x4_split(x_nchw, iw, ib, in_hi, in_lo, B, cfg.in_channel, H, W, c0, st); });
+      }
     }
     // which enc_feats the decoder loop reads: at quantising levels (before_quant input) and, in the LQ stage with
     // use_residual, at the other levels > 0 (skip adds)
@@ -764,6 +783,7 @@ extern "C" int femasr_net_create(const femasr_net_config* cfg, femasr_net** out)
   if (const char* ev = getenv("FEMASR_FAST_SILU")) n->fast_silu = atoi(ev) != 0;
   if (const char* ev = getenv("FEMASR_OUTCONV_MMA")) n->oc_mma = atoi(ev) != 0;
   if (const char* ev = getenv("FEMASR_VQ_FUSED")) n->vq_fused = atoi(ev) != 0;
+  if (const char* ev = getenv("FEMASR_IN_CONV_TC")) n->in_conv_tc = atoi(ev) != 0;
   if (const char* ev = getenv("FEMASR_TC_SLICE_KB")) n->tc_slice_kb = std::max(1, atoi(ev));
   build_spec(n);
   *out = n;
@@ -790,6 +810,18 @@ extern "C" int femasr_net_set_param(femasr_net* net, const char* name, const flo
     if (!pb.p) { FEMASR_CUDA(cudaMalloc(&pb.p, numel * sizeof(float))); pb.n = numel; }
     int s = femasr_pack_weight(rb.p, pb.p, pi.Cout, pi.Cin, pi.k, pi.k, st);
     if (s) return s;
+    if (net->cfg.gemm_path == 1 && net->in_conv_tc && pi.k == 4 && pi.Cin == 3 && pi.Cout % 64 == 0) {
+      // in_conv as a K = 48 -> 64 tensor-core GEMM over im2col rows: [Cout][64] padded matrix -> split-fp16 blob
+      float* tmp = nullptr;
+      FEMASR_CUDA(cudaMallocAsync(&tmp, (size_t)pi.Cout * 64 * sizeof(float), st));
+      s = femasr_in_conv_pad_weight(rb.p, tmp, pi.Cout, st);
+      DevBuf& tb = net->tcw[key + "#im2col"];
+      const size_t bytes = femasr_tc_weight_bytes(pi.Cout, 64, 1, 1);
+      if (!s && !tb.p) { if (cudaMalloc(&tb.p, bytes) != cudaSuccess) s = fail(FEMASR_ERR_CUDA, "cudaMalloc failed"); tb.n = bytes / sizeof(float); }
+      if (!s) s = femasr_tc_pack_weight(tmp, tb.p, pi.Cout, 64, 1, 1, st);
+      cudaFreeAsync(tmp, st);
+      return s;
+    }
     if (net->cfg.gemm_path == 1 && (pi.k == 1 || pi.k == 3) && pi.Cin % 64 == 0 && pi.Cout % 64 == 0) {
       DevBuf& tb = net->tcw[key];
       const size_t bytes = femasr_tc_weight_bytes(pi.Cout, pi.Cin, pi.k, pi.k);

@@ -214,14 +214,15 @@ struct TcCfg {
   static constexpr int B_RES_BYTES = BRES ? 9 * 2 * B_PLANE_BYTES : 0;
   static constexpr int SB_BYTES = 2 * B_PLANE_BYTES;
   static constexpr int NSPLIT = nsplit_for(BN), EPI_WARPS = 4 * NSPLIT, THREADS = tc_threads_for(BN);
-  static constexpr int SB_BUDGET = 232448 - 1024 - 256 - EPI_WARPS * 2048 - SA_STAGES * SA_BYTES;   // what is left of 227 KB
+  static constexpr int BIAS_BYTES = BN * 4;     // the n-tile's bias (VQ: sum e^2) staged in shared memory for the epilogue
+  static constexpr int SB_BUDGET = 232448 - 1024 - 256 - EPI_WARPS * 2048 - BIAS_BYTES - SA_STAGES * SA_BYTES;   // what is left of 227 KB
   static constexpr int SB_STAGES = BRES ? 0 : (SB_BUDGET / SB_BYTES > 6 ? 6 : SB_BUDGET / SB_BYTES);
   static constexpr int PIPE_BYTES = BRES ? B_RES_BYTES + SA_STAGES * SA_BYTES
                                          : (STRIP ? SA_STAGES * SA_BYTES + SB_STAGES * SB_BYTES : STAGES * STAGE_BYTES);
   // full/empty barriers of the rings (resident weights: one "weights landed" barrier instead of a weight ring)
   static constexpr int NBAR_PIPE = BRES ? 2 * SA_STAGES + 1 : (STRIP ? 2 * SA_STAGES + 2 * SB_STAGES : 2 * STAGES);
   static constexpr int EPI_BYTES = EPI_WARPS * 2048 /*per-warp 32x16 fp32 transpose tiles*/;
-  static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+  static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES + BIAS_BYTES;
   // Multi-row strip tiles (resident weights): one work item = MR vertically adjacent image rows of 128 pixels, each its
   // own 128 x BN accumulator.  Input row s (of MR + 2) is loaded ONCE and feeds the kh = s - r tap row of every output
   // row r it touches, so a tile streams (MR + 2) / MR strips per output row instead of 3 (L2 -> SM traffic / 2 at MR = 4)
@@ -566,6 +567,21 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const float inv_scale = __ldg(p.inv_scale);
     const uint32_t epi_base = bar_base + 256;
     float* stage = reinterpret_cast<float*>(smem_raw + (epi_base + (uint32_t)e * 2048u - smem_u32(smem_raw)));
+    // Per-column epilogue constants (bias; VQ: sum e^2) of the current n-tile live in shared memory: with the whole
+    // 227 KB carved out for the pipeline there is no L1 left, and a global load per 16-column chunk was the top stall
+    // of the short-K layers (16 % long-scoreboard, profiles/swin_kernels_ncu_r1.json).  Restaged only when the n-tile
+    // changes; two named barriers order the rewrite against the other epilogue warps' reads.
+    float* sbias = reinterpret_cast<float*>(smem_raw + (epi_base + (uint32_t)Cfg::EPI_BYTES - smem_u32(smem_raw)));
+    int staged_nt = -1;
+    auto stage_cols = [&](const float* src, int nt) {
+      if (nt == staged_nt) return;
+      const int et = (int)threadIdx.x - 128;
+      const float v = et < BN ? __ldg(src + nt * BN + et) : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * Cfg::EPI_WARPS) : "memory");
+      if (et < BN) sbias[et] = v;
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * Cfg::EPI_WARPS) : "memory");
+      staged_nt = nt;
+    };
     const int q = lane & 3, rsub = lane >> 2;
     constexpr int CW = BN / Cfg::NSPLIT;             // accumulator columns per warp
     constexpr int CH = 16, NCH = CW / CH;            // chunks per warp
@@ -604,6 +620,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           tj0 = tj1 = tj2 = tj3 = 0x7fffffff;
           a_row = valid ? __ldg(p.vq_a + token) : 0.f;
         }
+        stage_cols(p.vq_esq, tc.nt);
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + part * CW);
@@ -612,10 +629,10 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         for (int ci = 0; ci < NCH; ++ci) {
           uint32_t r[16];
           tmem_ld16(t_row + (uint32_t)(ci * CH), r);
-          const float4* es4 = reinterpret_cast<const float4*>(p.vq_esq + colbase + ci * CH);
+          const float4* es4 = reinterpret_cast<const float4*>(sbias + part * CW + ci * CH);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 es = __ldg(es4 + q4);
+            const float4 es = es4[q4];
             const float ee[4] = {es.x, es.y, es.z, es.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -673,6 +690,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         for (int it = 0; it < 4; ++it)
           cur[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.res1 + offs[it]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      if (p.bias) stage_cols(p.bias, nt);
       // sliced accumulation: fold all but the last partial into the running sum S (second TMEM buffer)
       const uint32_t t_sum = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(BN + part * CW);
       for (int s = 0; s + 1 < nslices; ++s) {
@@ -722,7 +740,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           o.x = __uint_as_float(r[4 * j]) * inv_scale; o.y = __uint_as_float(r[4 * j + 1]) * inv_scale;
           o.z = __uint_as_float(r[4 * j + 2]) * inv_scale; o.w = __uint_as_float(r[4 * j + 3]) * inv_scale;
           if (p.bias) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c + 4 * j));
+            const float4 bv = *reinterpret_cast<const float4*>(sbias + part * CW + c + 4 * j);
             o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
           }
           if (p.act == FEMASR_ACT_GELU) { o.x = gelu_erf_fast_f(o.x); o.y = gelu_erf_fast_f(o.y); o.z = gelu_erf_fast_f(o.z); o.w = gelu_erf_fast_f(o.w); }

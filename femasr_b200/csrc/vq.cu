@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict_
                                                         const float* __restrict__ esq, int64_t* __restrict__ idx,
                                                         float* __restrict__ zq, float* __restrict__ loss_rows,
                                                         unsigned int* __restrict__ stats, int N, int n_e, int e_dim) {
+  __shared__ __align__(16) float zs[8][1024];           // z rows of the (rare) whole-codebook rescans; e_dim <= 1024
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= N) return;
   const int lane = threadIdx.x & 31;
@@ -111,9 +112,30 @@ __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict_
       float best = INFINITY;
       int bb = 0x7fffffff;
       if (nc == 4) {
-        for (int c = 0; c < n_e; ++c) {                // candidate list overflowed: exact scan, increasing code
-          const float dd = vq_exact_distance(zr, codebook + (long)c * e_dim, ar, __ldg(esq + c), e_dim, lane);
+        // candidate list overflowed: exact scan of the whole codebook.  The z row goes to shared memory and every lane
+        // walks its own codes (lane, lane + 32, ...: increasing, so '<' keeps the lowest index) with four independent
+        // fp64 chains - no shuffles on the critical path; then a lexicographic (d, code) warp reduction.
+        float* zw = zs[threadIdx.x >> 5];
+        for (int k = lane; k < e_dim; k += 32) zw[k] = zr[k];
+        __syncwarp();
+        for (int c = lane; c < n_e; c += 32) {
+          const float4* er4 = reinterpret_cast<const float4*>(codebook + (long)c * e_dim);
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+          for (int k4 = 0; k4 < e_dim / 4; ++k4) {
+            const float4 ev = __ldg(er4 + k4);
+            const float4 zv = *reinterpret_cast<const float4*>(zw + 4 * k4);
+            s0 = fma((double)zv.x, (double)ev.x, s0); s1 = fma((double)zv.y, (double)ev.y, s1);
+            s2 = fma((double)zv.z, (double)ev.z, s2); s3 = fma((double)zv.w, (double)ev.w, s3);
+          }
+          const float cc = (float)((s0 + s1) + (s2 + s3));
+          const float dd = __fsub_rn(__fadd_rn(ar, __ldg(esq + c)), __fmul_rn(2.0f, cc));
           if (dd < best) { best = dd; bb = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float od = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oj = __shfl_xor_sync(0xffffffffu, bb, o);
+          if (od < best || (od == best && oj < bb)) { best = od; bb = oj; }
         }
       } else {
         for (int k = 0; k < nc; ++k) {
@@ -277,7 +299,7 @@ extern "C" int femasr_vq_finish(const float* z, const float* a, const void* cand
                                 int64_t* idx, float* zq, float* loss_rows, unsigned int* stats, int N, int n_e, int e_dim,
                                 void* stream) {
   FEMASR_CHECK_ARG(z && a && cand && codebook && esq, "vq_finish: null pointer");
-  FEMASR_CHECK_ARG(N > 0 && n_e > 0 && e_dim > 0, "vq_finish: empty problem");
+  FEMASR_CHECK_ARG(N > 0 && n_e > 0 && e_dim > 0 && e_dim <= 1024 && e_dim % 4 == 0, "vq_finish: e_dim must be a multiple of 4, at most 1024");
   vq_finish_kernel<<<(unsigned)cdiv(N, 8), 256, 0, as_stream(stream)>>>(z, a, reinterpret_cast<const uint2*>(cand), codebook, esq,
                                                                         idx, zq, loss_rows, stats, N, n_e, e_dim);
   return launch_status("vq_finish_kernel");

@@ -105,6 +105,8 @@ SIGNATURES = {
     "femasr_codebook_gather": (_I, [_V, _V, _V, _I, _I, _I, _V]),
     "femasr_in_conv4x4": (_I, [_V, _V, _V, _V, _I, _I, _I, _I, _I, _V]),
     "femasr_in_conv4x4_split": (_I, [_V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _V]),
+    "femasr_in_conv_im2col": (_I, [_V, _V, _V, _I, _I, _I, _I, _V]),
+    "femasr_in_conv_pad_weight": (_I, [_V, _V, _I, _V]),
     "femasr_out_conv3x3": (_I, [_V, _V, _V, _V, _I, _I, _I, _I, _V]),
     "femasr_out_conv3x3_mma": (_I, [_V, _V, _V, _V, _I, _I, _I, _I, _V]),
     "femasr_nchw_to_nhwc": (_I, [_V, _V, _I, _I, _I, _I, _V]),

@@ -294,6 +294,11 @@ int femasr_in_conv4x4(const float* x_nchw, const float* w, const float* bias, fl
 /* same, but the result is written as the split fp16 operand planes of the following tensor-core conv */
 int femasr_in_conv4x4_split(const float* x_nchw, const float* w, const float* bias, void* y_hi, void* y_lo, int B,
                             int Cin, int H, int W, int Cout, void* stream);
+/* in_conv on the tensor cores (femasr_arch.py:150): femasr_in_conv_im2col writes, per output pixel of the 4x4 p1 conv,
+ * its 48 input values (k = (kh*4+kw)*3+ci, zero padded to 64) as split fp16 planes [B*(H-1)*(W-1)][64]; the conv is then
+ * femasr_tc_igemm with ksize 1, Cin 64 on a weight blob packed from femasr_in_conv_pad_weight's [Cout][64] matrix. */
+int femasr_in_conv_im2col(const float* x_nchw, void* a_hi, void* a_lo, int B, int Cin, int H, int W, void* stream);
+int femasr_in_conv_pad_weight(const float* w_oihw, float* w_padded, int Cout, void* stream);
 /* out_conv (femasr_arch.py:273): 3x3 pad 1, NHWC [B,H,W,Cin] -> NCHW [B,3,H,W].  w packed [9*Cin][3]. */
 int femasr_out_conv3x3(const float* x_nhwc, const float* w, const float* bias, float* y_nchw, int B,
                        int H, int W, int Cin, void* stream);
