@@ -332,7 +332,9 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::NBAR_PIPE; ++s) mbar_init(bar_base + 8u * s, 1);
-    for (int a = 0; a < NACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * 32 * Cfg::EPI_WARPS); }
+    // tmem-empty: ONE arrival per epilogue warp (of both CTAs when paired), by an elected lane after __syncwarp - 512
+    // per-thread arrivals per tile were 512 remote DSMEM transactions for the peer CTA of a pair
+    for (int a = 0; a < NACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * Cfg::EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (PAIR) cluster_sync_all(); else __syncthreads();
@@ -589,8 +591,9 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const bool sliced = p.slice_kb > 0;
     const int nslices = sliced ? (p.kb_end - p.kb_begin + p.slice_kb - 1) / p.slice_kb : 1;
     // the MMA issuer waits on the LEADER's tmem-empty barriers; the peer's epilogue arrives there remotely
-    auto release_acc = [&](int a) {
-      if (PAIR) mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0)); else mbar_arrive(tempty_bar(a));
+    auto release_acc = [&](int a) {          // call with the whole warp converged, after tcgen05.wait::ld + fence::before
+      __syncwarp();
+      if (lane == 0) { if (PAIR) mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0)); else mbar_arrive(tempty_bar(a)); }
     };
     if constexpr (VQ) {
       // ===================== VQ epilogue: running top-4 of d_j = fl(fl(A + B_j) - 2 C_j) per feature row =====================

@@ -67,9 +67,14 @@ __global__ void __launch_bounds__(256) vq_select_kernel(const float* __restrict_
 // codebook is rescanned exactly.  The tensor-core distance differs from the exact one by at most one grid step
 // (|dC| ~ 1e-8 against ulp(A) ~ 3e-5), so the true argmin is always within 2 steps of the tensor-core best.
 // Then: gather, straight-through residual z + (e - z), per-row loss (femasr_arch.py:67-100).
-// Margin: 8 grid steps of the fp32 distance formula (the grid is ulp(A + B), not ulp(d): the subtraction may cancel) plus
-// twice a generous bound of the tensor-core error of 2C (3 * e_dim / 16 truncating accumulations of <= 1 ulp each).
-constexpr float VQ_MARGIN_ULPS = 8.0f;
+// Margin.  With u = the grid step of the fp32 distance formula (ulp of max(A + B, d): the subtraction may cancel) and a
+// tensor-core error of 2C far below u, tensor-core and exact distance of one code differ by at most u, so the true
+// argmin (and every exact tie with a lower index) lies within 2u of the tensor-core best: 2.5 u is used, plus four times a
+// bound of the tensor-core error of 2C itself (3 * e_dim / 16 truncating accumulations of <= 1 ulp each).
+constexpr float VQ_MARGIN_ULPS = 2.5f;
+__device__ __forceinline__ float ulp_of(float x) {      // spacing of fp32 numbers at |x| (normal range)
+  return __uint_as_float(__float_as_uint(x) & 0x7f800000u) * 1.1920929e-7f;
+}
 __device__ __forceinline__ float vq_exact_distance(const float* __restrict__ zr, const float* __restrict__ er, float a,
                                                     float b, int e_dim, int lane) {
   double s = 0.0;
@@ -102,7 +107,7 @@ __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict_
   } else {
     const float ar0 = a[r];
     const float ab0 = ar0 + __ldg(esq + bj);
-    const float margin = VQ_MARGIN_ULPS * 1.1920929e-7f * fmaxf(fabsf(ab0), fabsf(d[0])) +
+    const float margin = VQ_MARGIN_ULPS * ulp_of(fmaxf(fabsf(ab0), fabsf(d[0]))) +
                          4.0f * 1.1920929e-7f * (float)(3 * e_dim / 16) * fabsf(ab0 - d[0]) + 1e-30f;
     int nc = 1;
 #pragma unroll
@@ -121,11 +126,16 @@ __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict_
         for (int c = lane; c < n_e; c += 32) {
           const float4* er4 = reinterpret_cast<const float4*>(codebook + (long)c * e_dim);
           double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-          for (int k4 = 0; k4 < e_dim / 4; ++k4) {
-            const float4 ev = __ldg(er4 + k4);
-            const float4 zv = *reinterpret_cast<const float4*>(zw + 4 * k4);
-            s0 = fma((double)zv.x, (double)ev.x, s0); s1 = fma((double)zv.y, (double)ev.y, s1);
-            s2 = fma((double)zv.z, (double)ev.z, s2); s3 = fma((double)zv.w, (double)ev.w, s3);
+          for (int k4 = 0; k4 < e_dim / 4; k4 += 8) {          // e_dim % 32 == 0 (multiple of 64): 8 row loads in flight
+            float4 ev[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) ev[u] = __ldg(er4 + k4 + u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float4 zv = *reinterpret_cast<const float4*>(zw + 4 * (k4 + u));
+              s0 = fma((double)zv.x, (double)ev[u].x, s0); s1 = fma((double)zv.y, (double)ev[u].y, s1);
+              s2 = fma((double)zv.z, (double)ev[u].z, s2); s3 = fma((double)zv.w, (double)ev[u].w, s3);
+            }
           }
           const float cc = (float)((s0 + s1) + (s2 + s3));
           const float dd = __fsub_rn(__fadd_rn(ar, __ldg(esq + c)), __fmul_rn(2.0f, cc));
@@ -299,7 +309,7 @@ extern "C" int femasr_vq_finish(const float* z, const float* a, const void* cand
                                 int64_t* idx, float* zq, float* loss_rows, unsigned int* stats, int N, int n_e, int e_dim,
                                 void* stream) {
   FEMASR_CHECK_ARG(z && a && cand && codebook && esq, "vq_finish: null pointer");
-  FEMASR_CHECK_ARG(N > 0 && n_e > 0 && e_dim > 0 && e_dim <= 1024 && e_dim % 4 == 0, "vq_finish: e_dim must be a multiple of 4, at most 1024");
+  FEMASR_CHECK_ARG(N > 0 && n_e > 0 && e_dim > 0 && e_dim <= 1024 && e_dim % 32 == 0, "vq_finish: e_dim must be a multiple of 32, at most 1024");
   vq_finish_kernel<<<(unsigned)cdiv(N, 8), 256, 0, as_stream(stream)>>>(z, a, reinterpret_cast<const uint2*>(cand), codebook, esq,
                                                                         idx, zq, loss_rows, stats, N, n_e, e_dim);
   return launch_status("vq_finish_kernel");
