@@ -91,6 +91,14 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// L2 prefetch of a tensor box (no shared-memory destination, no barrier): issued a few pipeline stages ahead of the
+// real load so that the load finds its lines in L2.  The activation planes stream from HBM (2.1 GB per tensor at batch
+// 32), a load that misses L2 takes ~3 us under load, and the shared memory left next to resident weights holds only
+// two strip stages: without the prefetch the 64 -> 64 convs were latency-bound at 48 % tensor-pipe activity (ncu).
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -389,6 +397,17 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         tma_load_2d(smem_base + tap * 2 * Cfg::B_PLANE_BYTES + Cfg::B_PLANE_BYTES, &map_b_lo, bres_bar, tap * p.Cin, 0);
       }
     }
+    // L2 prefetch cursor: runs PF_STRIPS strips ahead of the loads over the same (work, input row, chunk) sequence
+    constexpr int PF_STRIPS = 4;
+    int pf_work = worker, pf_sr = 0, pf_cc = 0;
+    auto prefetch_next = [&]() {
+      if (pf_work >= num_work) return;
+      const TileCoord t = decode(pf_work);
+      tma_prefetch_4d(&map_a_hi, pf_cc * TC_BK, t.tx * p.Wt - 1, t.ty * MR + pf_sr - 1, t.b);
+      tma_prefetch_4d(&map_a_lo, pf_cc * TC_BK, t.tx * p.Wt - 1, t.ty * MR + pf_sr - 1, t.b);
+      if (++pf_cc == p.cchunks) { pf_cc = 0; if (++pf_sr == MR + 2) { pf_sr = 0; pf_work += nworkers; } }
+    };
+    for (int i = 0; i < PF_STRIPS; ++i) prefetch_next();
     for (int work = worker; work < num_work; work += nworkers) {
       const TileCoord tc = decode(work);
       const int x0 = tc.tx * p.Wt, y0 = tc.ty * MR, n0 = tc.nt * BN;
@@ -396,6 +415,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       for (int sr = 0; sr < MR + 2; ++sr)
         for (int cc = 0; cc < p.cchunks; ++cc) {
           const int c0 = cc * TC_BK;
+          prefetch_next();
           mbar_wait(emptyA_bar(sa), pa ^ 1u);
           const uint32_t a_dst = smem_base + Cfg::B_RES_BYTES + sa * Cfg::SA_BYTES;
           mbar_expect_tx(fullA_bar(sa), 2 * STRIP_PX * TC_BK * 2);
@@ -475,31 +495,52 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   } else if (!STRIP && warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     int stage = 0; uint32_t phase = 0;
+    // activation box of k-block kb of a tile: channel chunk and the tap's spatial offset (conv padding = TMA zero fill)
+    struct ABox { int c0, x, y, b, tap; };
+    auto a_box = [&](const TileCoord& tc, int kb) {
+      ABox bx;
+      bx.tap = kb / p.cchunks;
+      bx.c0 = (kb - bx.tap * p.cchunks) * TC_BK;
+      int dy = 0, dx = 0;
+      if (p.up) { dy = (bx.tap >> 1) - 1 + (tc.ph >> 1); dx = (bx.tap & 1) - 1 + (tc.ph & 1); }
+      else if (ksz == 3) { dy = bx.tap / 3 - 1; dx = bx.tap - (bx.tap / 3) * 3 - 1; }
+      bx.x = p.stride * tc.tx * p.Wt + dx; bx.y = p.stride * tc.ty * p.Ht + dy; bx.b = tc.b;
+      return bx;
+    };
+    // L2 prefetch cursor PF_KB k-blocks ahead of the loads (activations only: the weights are L2 residents anyway)
+    constexpr int PF_KB = 4;
+    int pf_it = 0, pf_kb = p.kb_begin;
+    auto prefetch_next = [&]() {
+      const int w = work_of(pf_it);
+      if (w < 0) return;
+      const TileCoord t = decode(w);
+      const ABox bx = a_box(t, pf_kb);
+      tma_prefetch_4d(&map_a_hi, bx.c0, bx.x, bx.y, bx.b);
+      tma_prefetch_4d(&map_a_lo, bx.c0, bx.x, bx.y, bx.b);
+      if (++pf_kb == p.kb_end) { pf_kb = p.kb_begin; ++pf_it; }
+    };
+    for (int i = 0; i < PF_KB; ++i) prefetch_next();
     for (int it = 0, work; (work = work_of(it)) >= 0; ++it) {
       const TileCoord tc = decode(work);
-      const int py = tc.ph >> 1, px = tc.ph & 1;
-      const int x0 = tc.tx * p.Wt, y0 = tc.ty * p.Ht;
       const int n0 = tc.ph * p.Cout + tc.nt * BN + (PAIR ? (int)rank * (BN / 2) : 0);
       for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
-        const int tap = kb / p.cchunks;
-        const int c0 = (kb - tap * p.cchunks) * TC_BK;
-        int dy = 0, dx = 0;
-        if (p.up) { dy = (tap >> 1) - 1 + py; dx = (tap & 1) - 1 + px; }
-        else if (ksz == 3) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
+        const ABox bx = a_box(tc, kb);
+        const int tap = bx.tap, c0 = bx.c0;
+        prefetch_next();
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
         if (PAIR) {
           // both CTAs' loads complete on the LEADER's barrier, armed once for the bytes of both
           const uint32_t lead_full = map_to_cta(full_bar(stage), 0);
           if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
-          tma2_load_4d(sa, &map_a_hi, lead_full, c0, p.stride * x0 + dx, p.stride * y0 + dy, tc.b);
-          tma2_load_4d(sa + A_PLANE_BYTES, &map_a_lo, lead_full, c0, p.stride * x0 + dx, p.stride * y0 + dy, tc.b);
+          tma2_load_4d(sa, &map_a_hi, lead_full, c0, bx.x, bx.y, bx.b);
+          tma2_load_4d(sa + A_PLANE_BYTES, &map_a_lo, lead_full, c0, bx.x, bx.y, bx.b);
           tma2_load_2d(sa + 2 * A_PLANE_BYTES, &map_b_hi, lead_full, tap * p.Cin + c0, n0);
           tma2_load_2d(sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &map_b_lo, lead_full, tap * p.Cin + c0, n0);
         } else {
           mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-          tma_load_4d(sa, &map_a_hi, full_bar(stage), c0, p.stride * x0 + dx, p.stride * y0 + dy, tc.b);
-          tma_load_4d(sa + A_PLANE_BYTES, &map_a_lo, full_bar(stage), c0, p.stride * x0 + dx, p.stride * y0 + dy, tc.b);
+          tma_load_4d(sa, &map_a_hi, full_bar(stage), c0, bx.x, bx.y, bx.b);
+          tma_load_4d(sa + A_PLANE_BYTES, &map_a_lo, full_bar(stage), c0, bx.x, bx.y, bx.b);
           tma_load_2d(sa + 2 * A_PLANE_BYTES, &map_b_hi, full_bar(stage), tap * p.Cin + c0, n0);
           tma_load_2d(sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &map_b_lo, full_bar(stage), tap * p.Cin + c0, n0);
         }
@@ -729,6 +770,8 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           for (int it = 0; it < 4; ++it)
             nxt[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.res1 + offs[it] + c + CH) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        // this lane's 4 columns of the chunk in the coalesced phase: [c + 4q, c + 4q + 4)
+        const float4 bq = p.bias ? *reinterpret_cast<const float4*>(sbias + part * CW + c + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t r[16];
         tmem_ld16(t_row + (uint32_t)c, r);
         if (nslices > 1) {
@@ -737,31 +780,45 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
           for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(sr[j]));
         }
+        // phase 1: the raw accumulators go straight into the (XOR-swizzled) transpose tile; scale, bias, GELU and the
+        // residual adds all happen in the coalesced layout below, where a lane owns the same 4 columns in all four row
+        // groups: ONE bias float4 per chunk (requested before the TMEM load), no shared-memory latency inside the math.
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float4 o;
-          o.x = __uint_as_float(r[4 * j]) * inv_scale; o.y = __uint_as_float(r[4 * j + 1]) * inv_scale;
-          o.z = __uint_as_float(r[4 * j + 2]) * inv_scale; o.w = __uint_as_float(r[4 * j + 3]) * inv_scale;
-          if (p.bias) {
-            const float4 bv = *reinterpret_cast<const float4*>(sbias + part * CW + c + 4 * j);
-            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-          }
-          if (p.act == FEMASR_ACT_GELU) { o.x = gelu_erf_fast_f(o.x); o.y = gelu_erf_fast_f(o.y); o.z = gelu_erf_fast_f(o.z); o.w = gelu_erf_fast_f(o.w); }
-          *reinterpret_cast<float4*>(&stage[lane * 16 + 4 * (j ^ ((lane >> 1) & 3))]) = o;
-        }
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(&stage[lane * 16 + 4 * (j ^ ((lane >> 1) & 3))]) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
-        float sa = 0.f, ssa = 0.f, sb = 0.f, ssb = 0.f;   // GroupNorm partials of channels (x,y) and (z,w)
+        // phase 2: all four row groups are read before any is stored - distinct registers, so a store's operands are
+        // never the destination of the next load (ncu: the single-register version spent 18 % of the qkv epilogue in
+        // long-scoreboard stalls behind its own stores)
+        float4 o4[4];
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int rr = it * 8 + rsub;
+          o4[it] = *reinterpret_cast<const float4*>(&stage[rr * 16 + 4 * (q ^ ((rr >> 1) & 3))]);
+        }
+        float sa = 0.f, ssa = 0.f, sb = 0.f, ssb = 0.f;   // GroupNorm partials of channels (x,y) and (z,w)
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          float4 o = o4[it];
+          o.x = fmaf(o.x, inv_scale, bq.x); o.y = fmaf(o.y, inv_scale, bq.y);      // acc * 2^-s is exact: == (acc * inv) + bias
+          o.z = fmaf(o.z, inv_scale, bq.z); o.w = fmaf(o.w, inv_scale, bq.w);
+          if (p.act == FEMASR_ACT_GELU) { o.x = gelu_erf_fast_f(o.x); o.y = gelu_erf_fast_f(o.y); o.z = gelu_erf_fast_f(o.z); o.w = gelu_erf_fast_f(o.w); }
+          if (RES) { o.x += cur[it].x; o.y += cur[it].y; o.z += cur[it].z; o.w += cur[it].w; }
+          o4[it] = o;
+        }
+        if (p.res2) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            if (offs[it] >= 0) {
+              const float4 rv = *reinterpret_cast<const float4*>(p.res2 + offs[it] + c);
+              o4[it].x += rv.x; o4[it].y += rv.y; o4[it].z += rv.z; o4[it].w += rv.w;
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
           if (offs[it] >= 0) {
             const long off = offs[it] + c;
-            float4 o = *reinterpret_cast<const float4*>(&stage[rr * 16 + 4 * (q ^ ((rr >> 1) & 3))]);
-            if (RES) { o.x += cur[it].x; o.y += cur[it].y; o.z += cur[it].z; o.w += cur[it].w; }
-            if (p.res2) {
-              const float4 rv = *reinterpret_cast<const float4*>(p.res2 + off);
-              o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-            }
+            const float4 o = o4[it];
             if (p.gn_partial) {
               sa += o.x + o.y; ssa = fmaf(o.x, o.x, fmaf(o.y, o.y, ssa));
               sb += o.z + o.w; ssb = fmaf(o.z, o.z, fmaf(o.w, o.w, ssb));
