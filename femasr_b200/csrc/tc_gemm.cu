@@ -99,6 +99,20 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, 
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// One lane of a converged warp (elect.sync).  The single-thread roles (TMA producer, MMA issuer) are entered through this
+// instead of `lane == 0`: with a data-dependent lane test ptxas must assume several lanes with different operands may be
+// active and wraps EVERY UTCHMMA / UTMALDG in an ELECT ... BRA.U.ANY serialisation loop with R2UR moves (~10 SASS
+// instructions and a branch per MMA); a 128x64x16 MMA is only 32 tensor-pipe cycles, so the issuing thread - not the
+// tensor core - paced the 64-wide convs (ncu: 48 % tensor-pipe activity, no memory or epilogue limiter).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -384,7 +398,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     return tc;
   };
 
-  if (STRIP && warp == 0 && lane == 0) {
+  if (STRIP && warp == 0 && elect_one()) {
     // ===================== TMA producer (strip mode) =====================
     // per (kh, 64-channel chunk): one 130-pixel activation strip (hi, lo), then the three taps' weight tiles
     int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
@@ -398,7 +412,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       }
     }
     // L2 prefetch cursor: runs PF_STRIPS strips ahead of the loads over the same (work, input row, chunk) sequence
-    constexpr int PF_STRIPS = 4;
+    constexpr int PF_STRIPS = BRES ? 4 : 0;      // 128 -> 128 strips (streamed weights, deeper rings): measured neutral
     int pf_work = worker, pf_sr = 0, pf_cc = 0;
     auto prefetch_next = [&]() {
       if (pf_work >= num_work) return;
@@ -415,7 +429,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       for (int sr = 0; sr < MR + 2; ++sr)
         for (int cc = 0; cc < p.cchunks; ++cc) {
           const int c0 = cc * TC_BK;
-          prefetch_next();
+          if (PF_STRIPS > 0) prefetch_next();
           mbar_wait(emptyA_bar(sa), pa ^ 1u);
           const uint32_t a_dst = smem_base + Cfg::B_RES_BYTES + sa * Cfg::SA_BYTES;
           mbar_expect_tx(fullA_bar(sa), 2 * STRIP_PX * TC_BK * 2);
@@ -435,7 +449,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           }
         }
     }
-  } else if (STRIP && warp == 1 && lane == 0) {
+  } else if (STRIP && warp == 1 && elect_one()) {
     // ===================== MMA issuer (strip mode) =====================
     const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
@@ -492,7 +506,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         }
       if (++set == 2) { set = 0; set_phase ^= 1u; }
     }
-  } else if (!STRIP && warp == 0 && lane == 0) {
+  } else if (!STRIP && warp == 0 && elect_one()) {
     // ===================== TMA producer =====================
     int stage = 0; uint32_t phase = 0;
     // activation box of k-block kb of a tile: channel chunk and the tap's spatial offset (conv padding = TMA zero fill)
@@ -507,8 +521,13 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       bx.x = p.stride * tc.tx * p.Wt + dx; bx.y = p.stride * tc.ty * p.Ht + dy; bx.b = tc.b;
       return bx;
     };
-    // L2 prefetch cursor PF_KB k-blocks ahead of the loads (activations only: the weights are L2 residents anyway)
-    constexpr int PF_KB = 4;
+    // L2 prefetch cursor PF_KB k-blocks ahead of the loads (activations only: the weights are L2 residents anyway).
+    // Measured OFF (0): a prefetch box costs the TMA unit as much as a load, and with 2-4 joint stages of 48-96 KB these
+    // tiles are not load-latency bound - the sub-pixel up convs lost 20-40 % with PF_KB = 4 (profiles/microbench_r2_*).
+#ifndef FEMASR_PF_KB
+#define FEMASR_PF_KB 0
+#endif
+    constexpr int PF_KB = FEMASR_PF_KB;
     int pf_it = 0, pf_kb = p.kb_begin;
     auto prefetch_next = [&]() {
       const int w = work_of(pf_it);
@@ -526,7 +545,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
         const ABox bx = a_box(tc, kb);
         const int tap = bx.tap, c0 = bx.c0;
-        prefetch_next();
+        if (PF_KB > 0) prefetch_next();
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
         if (PAIR) {
@@ -547,7 +566,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (!STRIP && warp == 1 && lane == 0 && rank == 0) {
+  } else if (!STRIP && warp == 1 && rank == 0 && elect_one()) {
     // ===================== MMA issuer (leader CTA only when paired) =====================
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major both,
     // N>>3 at bits 17-22, M>>4 at bits 24-28 (M = 256 across the CTA pair).
