@@ -99,6 +99,16 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, 
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// TMA store of a shared-memory box to a global tensor (bulk async group of the issuing thread) and its fences / waits
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources reusable
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }          // writes complete
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // One lane of a converged warp (elect.sync).  The single-thread roles (TMA producer, MMA issuer) are entered through this
 // instead of `lane == 0`: with a data-dependent lane test ptxas must assume several lanes with different operands may be
 // active and wraps EVERY UTCHMMA / UTMALDG in an ELECT ... BRA.U.ANY serialisation loop with R2UR moves (~10 SASS
@@ -189,6 +199,8 @@ struct TcP {
   int slice_kb;                  // >0: in-kernel K slicing - every slice_kb k-blocks the accumulator is drained into an
                                  // fp32 running sum kept in the second TMEM buffer (round-to-nearest adds by the
                                  // epilogue warps), so the truncating MMA accumulator never runs longer than a slice
+  int tma_out;                   // 1: fp32 y, 2: split fp16 planes leave through TMA stores of the epilogue's staging tile
+  int box_w, box_w_shift;        // a warp's 32 accumulator rows as a box of box_w x (32 / box_w) output pixels
   // VQ mode (template VQ): the GEMM is z . E^T and the epilogue keeps, per feature row, the four smallest distances
   // fl(fl(A + B_j) - 2 C_j) over all codes instead of storing the [N, n_e] product (femasr_arch.py:35-38, 63-66)
   const float* vq_a;             // [M]   A = sum z^2 per row
@@ -256,6 +268,7 @@ struct TcCfg {
   static_assert(TMEM_COLS <= 512, "TMEM budget");
   static_assert(8 * (NBAR_PIPE + 2 * NACC) + 4 <= 256, "barrier area");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(PIPE_BYTES % 1024 == 0, "the epilogue staging tiles must start on the swizzle period");
   static_assert(!STRIP || BRES || SB_STAGES >= 2, "strip weight ring too small");
 };
 
@@ -310,12 +323,15 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
 template <int BN, bool PAIR, bool STRIP, bool BRES, bool RES, bool VQ = false>
 __global__ void __launch_bounds__(tc_threads_for(BN), 1)
 tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcP p) {
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_oh,
+                const __grid_constant__ CUtensorMap map_ol, const TcP p) {
   using Cfg = TcCfg<BN, PAIR, STRIP, BRES>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::PIPE_BYTES;
+  const uint32_t epi_base = smem_base + Cfg::PIPE_BYTES;           // 1024-aligned: the staging tiles are TMA-store sources
+  const uint32_t bar_base = epi_base + Cfg::EPI_BYTES + Cfg::BIAS_BYTES;
   // barriers: the ring barriers (joint: full[STAGES], empty[STAGES]; strip: fullA, emptyA, fullB, emptyB),
   // then tmem_full[2], tmem_empty[2]; then the TMEM base pointer
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -627,7 +643,6 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const int ew = e & 3, part = e >> 2;             // TMEM lane quarter, column part
     const int row = ew * 32 + lane;
     const float inv_scale = __ldg(p.inv_scale);
-    const uint32_t epi_base = bar_base + 256;
     float* stage = reinterpret_cast<float*>(smem_raw + (epi_base + (uint32_t)e * 2048u - smem_u32(smem_raw)));
     // Per-column epilogue constants (bias; VQ: sum e^2) of the current n-tile live in shared memory: with the whole
     // 227 KB carved out for the pipeline there is no L1 left, and a global load per 16-column chunk was the top stall
@@ -802,6 +817,10 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         // phase 1: the raw accumulators go straight into the (XOR-swizzled) transpose tile; scale, bias, GELU and the
         // residual adds all happen in the coalesced layout below, where a lane owns the same 4 columns in all four row
         // groups: ONE bias float4 per chunk (requested before the TMEM load), no shared-memory latency inside the math.
+        if (p.tma_out) {                                   // the previous chunk's bulk store must have read the tile
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<uint4*>(&stage[lane * 16 + 4 * (j ^ ((lane >> 1) & 3))]) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
@@ -833,23 +852,68 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
               o4[it].x += rv.x; o4[it].y += rv.y; o4[it].z += rv.z; o4[it].w += rv.w;
             }
         }
+        if (p.gn_partial) {
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          if (offs[it] >= 0) {
-            const long off = offs[it] + c;
-            const float4 o = o4[it];
-            if (p.gn_partial) {
+          for (int it = 0; it < 4; ++it)
+            if (offs[it] >= 0) {
+              const float4 o = o4[it];
               sa += o.x + o.y; ssa = fmaf(o.x, o.x, fmaf(o.y, o.y, ssa));
               sb += o.z + o.w; ssb = fmaf(o.z, o.z, fmaf(o.w, o.w, ssb));
             }
-            if (p.out_hi) {
+        }
+        if (p.tma_out) {
+          // The finished values go back into the staging tile and leave as ONE bulk tensor store per plane, issued by an
+          // elected lane: no per-thread global addresses, no LSU wavefronts per 64-byte row segment and - the point - no
+          // register held hostage by an unretired store (ncu: ~20 % of the epilogue's samples were long-scoreboard WAR
+          // stalls behind STG).  Rows / columns past the tensor edge are clipped by the TMA; dummy pair tiles carry an
+          // out-of-range image index and are dropped entirely.
+          const int r0 = ew * 32;                          // first accumulator row of this warp
+          const int bx = tx * p.Wt + (r0 & (p.Wt - 1)), by = ty * p.Ht + (r0 >> p.wt_shift);
+          const uint32_t st_addr = smem_u32(stage);
+          if (p.tma_out == 1) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + rsub;
+              *reinterpret_cast<float4*>(&stage[rr * 16 + 4 * (q ^ ((rr >> 1) & 3))]) = o4[it];     // in place: the cell this lane read
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_4d(&map_y, st_addr, col0 + c, bx, by, b); bulk_commit(); }
+          } else {
+            __syncwarp();                                  // every lane has read its fp32 cells before halves overwrite them
+            __half* sh = reinterpret_cast<__half*>(stage);   // hi plane [32][16] halves, then the lo plane
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + rsub;
               uint2 h, l;
-              split_pack2(o.x, o.y, h.x, l.x);
-              split_pack2(o.z, o.w, h.y, l.y);
-              *reinterpret_cast<uint2*>(p.out_hi + off) = h;
-              *reinterpret_cast<uint2*>(p.out_lo + off) = l;
-            } else {
-              *reinterpret_cast<float4*>(p.y + off) = o;
+              split_pack2(o4[it].x, o4[it].y, h.x, l.x);
+              split_pack2(o4[it].z, o4[it].w, h.y, l.y);
+              *reinterpret_cast<uint2*>(sh + rr * 16 + 4 * q) = h;
+              *reinterpret_cast<uint2*>(sh + 512 + rr * 16 + 4 * q) = l;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&map_oh, st_addr, col0 + c, bx, by, b);
+              tma_store_4d(&map_ol, st_addr + 1024, col0 + c, bx, by, b);
+              bulk_commit();
+            }
+          }
+        } else {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            if (offs[it] >= 0) {
+              const long off = offs[it] + c;
+              const float4 o = o4[it];
+              if (p.out_hi) {
+                uint2 h, l;
+                split_pack2(o.x, o.y, h.x, l.x);
+                split_pack2(o.z, o.w, h.y, l.y);
+                *reinterpret_cast<uint2*>(p.out_hi + off) = h;
+                *reinterpret_cast<uint2*>(p.out_lo + off) = l;
+              } else {
+                *reinterpret_cast<float4*>(p.y + off) = o;
+              }
             }
           }
         }
@@ -886,6 +950,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       else if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
     }
   }
+  if (warp >= 4 && lane == 0 && p.tma_out) bulk_wait_all();      // bulk stores read this CTA's shared memory
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
@@ -1106,21 +1171,25 @@ static EncodeTiledFn get_encode() {
 }
 
 static int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                    const cuuint32_t* box, int spatial_stride = 1) {
+                    const cuuint32_t* box, int spatial_stride = 1, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(FEMASR_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint32_t estr[4] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1};
   if (rank == 2) estr[1] = 1;
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = enc(m, dtype, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(FEMASR_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
   return FEMASR_OK;
 }
 
+// output maps of the TMA-store epilogue (valid when p.tma_out != 0; otherwise copies of an input map, never dereferenced)
+struct OutMaps { CUtensorMap y, oh, ol; };
+
 template <int BN, bool PAIR, bool STRIP, bool BRES, bool RES>
 static int launch_tc_v(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-                       const TcP& p, cudaStream_t st) {
+                       const OutMaps& om, const TcP& p, cudaStream_t st) {
   using Cfg = TcCfg<BN, PAIR, STRIP, BRES>;
   static PerDeviceFlag attr_set;      // per template instantiation AND per device
   if (!attr_set.cur()) {
@@ -1129,7 +1198,7 @@ static int launch_tc_v(const CUtensorMap& ah, const CUtensorMap& al, const CUten
   }
   if constexpr (!PAIR) {
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    tc_igemm_kernel<BN, false, STRIP, BRES, RES><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
+    tc_igemm_kernel<BN, false, STRIP, BRES, RES><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, om.y, om.oh, om.ol, p);
     return launch_status("tc_igemm_kernel");
   } else {
     const int num_m = p.num_tiles / p.n_tiles;
@@ -1142,16 +1211,16 @@ static int launch_tc_v(const CUtensorMap& ah, const CUtensorMap& al, const CUten
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    FEMASR_CUDA(cudaLaunchKernelEx(&cfg, tc_igemm_kernel<BN, true, false, false, RES>, ah, al, bh, bl, p));
+    FEMASR_CUDA(cudaLaunchKernelEx(&cfg, tc_igemm_kernel<BN, true, false, false, RES>, ah, al, bh, bl, om.y, om.oh, om.ol, p));
     return launch_status("tc_igemm_kernel(pair)");
   }
 }
 
 template <int BN, bool PAIR, bool STRIP, bool BRES = false>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-                     const TcP& p, cudaStream_t st) {
-  return p.res1 ? launch_tc_v<BN, PAIR, STRIP, BRES, true>(ah, al, bh, bl, p, st)
-                : launch_tc_v<BN, PAIR, STRIP, BRES, false>(ah, al, bh, bl, p, st);
+                     const OutMaps& om, const TcP& p, cudaStream_t st) {
+  return p.res1 ? launch_tc_v<BN, PAIR, STRIP, BRES, true>(ah, al, bh, bl, om, p, st)
+                : launch_tc_v<BN, PAIR, STRIP, BRES, false>(ah, al, bh, bl, om, p, st);
 }
 
 template <int BN>
@@ -1165,7 +1234,7 @@ static int launch_vq(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
   }
   const int num_m = p.num_tiles / p.n_tiles;
   const int grid = num_m < sm_count() ? num_m : sm_count();
-  tc_igemm_kernel<BN, false, false, false, false, true><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
+  tc_igemm_kernel<BN, false, false, false, false, true><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, ah, ah, ah, p);
   return launch_status("tc_igemm_kernel(vq)");
 }
 
@@ -1190,12 +1259,21 @@ static TilePlan plan_tiles(const femasr_tc_args* a, int H, int W) {
   const int stride = a->stride == 2 ? 2 : 1;
   const int taps = a->upsample ? 4 : a->ksize * a->ksize;
   t.BN = a->Cout % 256 == 0 ? 256 : (a->Cout % 128 == 0 ? 128 : 64);
+  // study knob: FEMASR_TC_BN caps the tile width (e.g. 128-wide tiles for the 256-wide layers)
+  static const int bn_env = [] { const char* e = getenv("FEMASR_TC_BN"); return e ? atoi(e) : 0; }();
+  if ((bn_env == 128 || bn_env == 64) && bn_env < t.BN && a->Cout % bn_env == 0) t.BN = bn_env;
   // CTA pairs (tcgen05 cta_group::2): a->pair 1 = on, 0 = off, -1 = automatic (FEMASR_TC_PAIR=0/1 overrides).
   // Measured (profiles/microbench_*): pairing pays when the weight tile is wide and the K loop long enough to
   // amortise the pair's coupling - BN = 256 and K >= 1024 (+10..22 %); narrow / short-K layers are faster unpaired.
   static const int pair_env = [] { const char* e = getenv("FEMASR_TC_PAIR"); return e ? atoi(e) : -1; }();
   const int pair_req = a->pair >= 0 ? a->pair : pair_env;
-  t.pair = pair_req >= 0 ? pair_req != 0 : (t.BN == 256 && (long)taps * a->Cin >= 1024);
+  // Round-2 sweep with the cheap (elect.sync) MMA issue (profiles/sweep_bn_pair_r2.txt): the plain fp32-output linears with
+  // three or more column tiles (qkv) also gain 5 % paired; fc1 (GELU + split epilogue, issue-bound) and proj do not.
+  const bool wide_plain_linear = a->ksize == 1 && a->act == FEMASR_ACT_NONE && a->y && a->Cout >= 768;
+  t.pair = pair_req >= 0 ? pair_req != 0 : (t.BN == 256 && ((long)taps * a->Cin >= 1024 || wide_plain_linear));
+  // K-sliced linears (fc2 in front of the VQ): 128-wide unpaired tiles - the accumulator drain of a slice is half as
+  // long and twice as many tiles overlap it (0.210 -> 0.197 ms)
+  if (bn_env == 0 && a->ksize == 1 && a->slice_kb > 0 && t.BN == 256 && pair_req < 0) { t.BN = 128; t.pair = false; }
   // strip mode (one activation strip shared by the three horizontal taps): a->strip 1/0/-1 like pair
   static const int strip_env = [] { const char* e = getenv("FEMASR_TC_STRIP"); return e ? atoi(e) : -1; }();
   const int strip_req = a->strip >= 0 ? a->strip : strip_env;
@@ -1421,18 +1499,46 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
     s = make_map(&mbl, w_lo, 2, dims, str, box);
     if (s) return s;
   }
+  // TMA-store epilogue: the output is a plain [B, H, W, Cout] tensor (no sub-pixel phases) -> the staging tile of each
+  // epilogue warp (32 accumulator rows x 16 columns) leaves as one bulk tensor store; edge tiles are clipped by the TMA
+  static const int tma_env = [] { const char* e = getenv("FEMASR_TMA_STORE"); return e ? atoi(e) : 1; }();
+  OutMaps om;
+  om.y = mah; om.oh = mah; om.ol = mah;
+  p.tma_out = 0;
+  p.box_w = p.Wt < 32 ? p.Wt : 32;
+  p.box_w_shift = 0; while ((1 << p.box_w_shift) < p.box_w) ++p.box_w_shift;
+  // Measured same-box A/B (profiles/microbench_r2_tma_store_ab.txt): linears +3..6 %, 64-wide strip convs -5..9 % (8
+  // epilogue warps: the extra staging write and the read-wait of the bulk store cost more than the stores they replace),
+  // other convs neutral -> enabled for ksize 1 only; FEMASR_TMA_STORE=2 forces it everywhere, 0 disables it.
+  if (tma_env && !a->upsample && (a->ksize == 1 || tma_env == 2)) {
+    const cuuint64_t dims[4] = {(cuuint64_t)a->Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint32_t box[4] = {16, (cuuint32_t)p.box_w, (cuuint32_t)(32 / p.box_w), 1};
+    if (a->y) {
+      const cuuint64_t str[3] = {(cuuint64_t)a->Cout * 4, (cuuint64_t)W * a->Cout * 4, (cuuint64_t)H * W * a->Cout * 4};
+      int s = make_map(&om.y, a->y, 4, dims, str, box, 1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (s) return s;
+      p.tma_out = 1;
+    } else {
+      const cuuint64_t str[3] = {(cuuint64_t)a->Cout * 2, (cuuint64_t)W * a->Cout * 2, (cuuint64_t)H * W * a->Cout * 2};
+      int s = make_map(&om.oh, a->out_hi, 4, dims, str, box, 1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_NONE);
+      if (s) return s;
+      s = make_map(&om.ol, a->out_lo, 4, dims, str, box, 1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_NONE);
+      if (s) return s;
+      p.tma_out = 2;
+    }
+  }
   cudaStream_t st = as_stream(stream);
   if (strip) {
-    if (BN == 128) return launch_tc<128, false, true>(mah, mal, mbh, mbl, p, st);
-    if (bres) return launch_tc<64, false, true, true>(mah, mal, mbh, mbl, p, st);
-    return launch_tc<64, false, true>(mah, mal, mbh, mbl, p, st);
+    if (BN == 128) return launch_tc<128, false, true>(mah, mal, mbh, mbl, om, p, st);
+    if (bres) return launch_tc<64, false, true, true>(mah, mal, mbh, mbl, om, p, st);
+    return launch_tc<64, false, true>(mah, mal, mbh, mbl, om, p, st);
   }
   if (pair) {
-    if (BN == 256) return launch_tc<256, true, false>(mah, mal, mbh, mbl, p, st);
-    if (BN == 128) return launch_tc<128, true, false>(mah, mal, mbh, mbl, p, st);
-    return launch_tc<64, true, false>(mah, mal, mbh, mbl, p, st);
+    if (BN == 256) return launch_tc<256, true, false>(mah, mal, mbh, mbl, om, p, st);
+    if (BN == 128) return launch_tc<128, true, false>(mah, mal, mbh, mbl, om, p, st);
+    return launch_tc<64, true, false>(mah, mal, mbh, mbl, om, p, st);
   }
-  if (BN == 256) return launch_tc<256, false, false>(mah, mal, mbh, mbl, p, st);
-  if (BN == 128) return launch_tc<128, false, false>(mah, mal, mbh, mbl, p, st);
-  return launch_tc<64, false, false>(mah, mal, mbh, mbl, p, st);
+  if (BN == 256) return launch_tc<256, false, false>(mah, mal, mbh, mbl, om, p, st);
+  if (BN == 128) return launch_tc<128, false, false>(mah, mal, mbh, mbl, om, p, st);
+  return launch_tc<64, false, false>(mah, mal, mbh, mbl, om, p, st);
 }
