@@ -156,6 +156,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// the same load without the wait: the registers are valid after tmem_wait_ld()
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+// the wait names the registers as in/out operands so that no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
@@ -264,7 +279,11 @@ struct TcCfg {
   // (all the shared memory the resident weights leave).
   static constexpr int MR = BRES ? 4 : 1;
   static constexpr int NACC = 2 * MR;                             // accumulator ring: two sets of MR
-  static constexpr int TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;   // power of two for BN in {64,128,256}
+  // K-sliced accumulation with a THIRD buffer (tiles up to 128 wide): the MMA ping-pongs between buffers 0 / 1 while the
+  // epilogue folds the finished partial into the running sum in buffer 2, so the tensor pipe no longer idles during a
+  // fold (ncu on the 2-buffer protocol: 41 % of the epilogue's samples waiting for the next partial, tensor pipe 51 %).
+  static constexpr bool S3 = !STRIP && BN <= 128;
+  static constexpr int TMEM_COLS = S3 ? 4 * BN : (NACC * BN < 32 ? 32 : NACC * BN);   // power of two for BN in {64,128,256}
   static_assert(TMEM_COLS <= 512, "TMEM budget");
   static_assert(8 * (NBAR_PIPE + 2 * NACC) + 4 <= 256, "barrier area");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -625,8 +644,9 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         }
         // (partial) accumulator complete -> epilogue warps (of both CTAs)
         if (PAIR) umma2_commit_mc(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
-        // sliced: one MMA target buffer (0), the other holds the running sum; else ping-pong the two accumulators
-        if (sliced) acc_phase ^= 1u;
+        // sliced, 256-wide: one MMA target buffer (0), the other holds the running sum; else ping-pong (tiles, or the
+        // partials of a sliced tile when a third buffer holds the sum)
+        if (sliced && !Cfg::S3) acc_phase ^= 1u;
         else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -770,12 +790,13 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       }
       if (p.bias) stage_cols(p.bias, nt);
       // sliced accumulation: fold all but the last partial into the running sum S (second TMEM buffer)
-      const uint32_t t_sum = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(BN + part * CW);
+      const uint32_t t_sum = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((Cfg::S3 ? 2 * BN : BN) + part * CW);
       for (int s = 0; s + 1 < nslices; ++s) {
-        mbar_wait(tfull_bar(0), acc_phase);
-        acc_phase ^= 1u;
+        const int fa = Cfg::S3 ? acc : 0;              // buffer holding this partial
+        mbar_wait(tfull_bar(fa), acc_phase);
+        if (!Cfg::S3) acc_phase ^= 1u;
         tc_fence_after();
-        const uint32_t t_part = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(part * CW);
+        const uint32_t t_part = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(fa * BN + part * CW);
 #pragma unroll 1
         for (int ci = 0; ci < NCH; ++ci) {
           uint32_t pr[16];
@@ -790,11 +811,13 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         }
         tmem_wait_st();
         tc_fence_before();
-        release_acc(0);
+        release_acc(fa);
+        if (Cfg::S3 && ++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + part * CW);
+      uint32_t rn[16];                                   // next chunk's accumulators (64-wide tiles only)
 #pragma unroll 1
       for (int ci = 0; ci < NCH; ++ci) {
         const int c = ci * CH;
@@ -806,8 +829,20 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         }
         // this lane's 4 columns of the chunk in the coalesced phase: [c + 4q, c + 4q + 4)
         const float4 bq = p.bias ? *reinterpret_cast<const float4*>(sbias + part * CW + c + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // 64-wide tiles (8 epilogue warps, registers to spare): the NEXT chunk's TMEM load is already in flight while this
+        // chunk goes through its transpose / math / store phases (the exposed tcgen05.ld latency was 9 % of the 64 -> 64
+        // conv's samples); the wide tiles sit at the 96-register cap of a 640-thread CTA and load on demand.
+        constexpr bool PIPE_LD = BN == 64;
         uint32_t r[16];
-        tmem_ld16(t_row + (uint32_t)c, r);
+        if (PIPE_LD && nslices == 1) {
+          if (ci == 0) tmem_ld16_async(t_row, rn);
+          tmem_wait_ld(rn);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = rn[j];
+          if (ci + 1 < NCH) tmem_ld16_async(t_row + (uint32_t)(c + CH), rn);
+        } else {
+          tmem_ld16(t_row + (uint32_t)c, r);
+        }
         if (nslices > 1) {
           uint32_t sr[16];
           tmem_ld16(t_sum + (uint32_t)c, sr);
@@ -945,8 +980,8 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         for (int it = 0; it < 4; ++it) if (RES) cur[it] = nxt[it];
       }
       tc_fence_before();
-      release_acc(acc);                         // 256 (512 when paired) arrivals release the accumulator
-      if (sliced) acc_phase ^= 1u;
+      release_acc(acc);                         // one arrival per epilogue warp releases the accumulator
+      if (sliced && !Cfg::S3) acc_phase ^= 1u;
       else if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
     }
   }

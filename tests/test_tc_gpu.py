@@ -143,7 +143,8 @@ def test_tc_k_sliced_accumulation(cuda):
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,kw", [
     (1, 24, 40, 256, 256, {}), (2, 16, 24, 128, 128, {}), (1, 33, 17, 128, 64, {}), (3, 64, 64, 64, 64, {}),
-    (1, 8, 8, 256, 256, {"upsample": 1}), (1, 31, 31, 256, 256, {"stride": 2}), (1, 24, 40, 256, 256, {"slice_kb": 4})])
+    (1, 8, 8, 256, 256, {"upsample": 1}), (1, 31, 31, 256, 256, {"stride": 2}), (1, 24, 40, 256, 256, {"slice_kb": 4}),
+    (2, 16, 24, 128, 128, {"slice_kb": 4})])        # 128-wide: the three-buffer sliced protocol over a CTA pair
 def test_tc_cta_pair(cuda, B, H, W, Cin, Cout, kw):
     """tcgen05 cta_group::2 variant (256-row tiles over a CTA pair, odd tile counts -> dummy second tile)."""
     x, w, b = rnd(B, Cin, H, W, seed=46), rnd(Cout, Cin, 3, 3, seed=47, scale=0.03), rnd(Cout, seed=48)
