@@ -130,30 +130,19 @@ __global__ void __launch_bounds__(128, FEMASR_ATTN_MINBLOCKS) window_attention_m
                                                                    const float* __restrict__ bias_frag,
                                                                    float* __restrict__ out, __half* __restrict__ out_hi,
                                                                    __half* __restrict__ out_lo, int H, int W, int C,
-                                                                   int heads, int shift, int nwin) {
+                                                                   int heads, int shift) {
   __shared__ __align__(16) __half Kh[WT * KV_LD], Kl[WT * KV_LD];   // [key][k-index]  (k-index = permuted head dim)
   __shared__ __align__(16) __half Vh[WT * KV_LD], Vl[WT * KV_LD];   // [key][permuted dim]
   __shared__ __align__(8) int region[WT];
   __shared__ long toks[WT];
-  // CTA = (head, window group): it walks its windows with the head's relative-position-bias fragments held in
-  // registers - one bias fetch (16 KB per CTA from L2) per ~16 windows instead of per window; the bias was a third of
-  // this kernel's L2 -> SM bytes.
   const int head = blockIdx.x % heads;
-  const int wgroup = blockIdx.x / heads, ngroups = gridDim.x / heads;
+  const int win = blockIdx.x / heads;
   const int nwx = W / WS, nwy = H / WS;
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
-  // this warp's bias fragments (independent of the window)
-  float4 bf[8];
-  {
-    const float4* bp = reinterpret_cast<const float4*>(bias_frag) + ((long)(head * 4 + warp) * 8) * 32 + lane;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) bf[nt] = __ldg(bp + nt * 32);
-  }
-  for (int win = wgroup; win < nwin; win += ngroups) {
   const int b = win / (nwx * nwy);
   const int wrem = win - b * nwx * nwy;
   const int wy = wrem / nwx, wx = wrem - wy * nwx;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
   {
     // staging: 8 consecutive threads fetch one token's 32 K (V) values; thread = (token tid/8 + 16 i, dims [4q, 4q+4))
     const int q = tid & 7;
@@ -185,6 +174,13 @@ __global__ void __launch_bounds__(128, FEMASR_ATTN_MINBLOCKS) window_attention_m
       *reinterpret_cast<uint32_t*>(&Vh[j * KV_LD + posA]) = h0; *reinterpret_cast<uint32_t*>(&Vh[j * KV_LD + posB]) = h1;
       *reinterpret_cast<uint32_t*>(&Vl[j * KV_LD + posA]) = l0; *reinterpret_cast<uint32_t*>(&Vl[j * KV_LD + posB]) = l1;
     }
+  }
+  // this warp's bias fragments (independent of the window): issue the loads before the barrier
+  float4 bf[8];
+  {
+    const float4* bp = reinterpret_cast<const float4*>(bias_frag) + ((long)(head * 4 + warp) * 8) * 32 + lane;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) bf[nt] = __ldg(bp + nt * 32);
   }
   __syncthreads();
 
@@ -302,8 +298,6 @@ __global__ void __launch_bounds__(128, FEMASR_ATTN_MINBLOCKS) window_attention_m
     *reinterpret_cast<float4*>(out + e1) = make_float4(o[0][2] * i1, o[0][3] * i1, o[1][2] * i1, o[1][3] * i1);
     *reinterpret_cast<float4*>(out + e1 + 4) = make_float4(o[2][2] * i1, o[2][3] * i1, o[3][2] * i1, o[3][3] * i1);
   }
-  __syncthreads();                                   // K / V / toks / region are restaged for the next window
-  }
 }
 
 // bias_full[h][i][j] = table[rel_index(i,j)][h],  rel_index = (yi-yj+7)*15 + (xi-xj+7)   (network_swinir.py:91-101,127-129)
@@ -352,15 +346,9 @@ extern "C" int femasr_window_attention_mma(const float* qkv, const float* bias_f
   FEMASR_CHECK_ARG(H % WS == 0 && W % WS == 0, "window_attention_mma: H and W must be multiples of the 8x8 window");
   FEMASR_CHECK_ARG(heads > 0 && C == heads * HD, "window_attention_mma: C must equal heads*32");
   FEMASR_CHECK_ARG(shift == 0 || shift == WS / 2, "window_attention_mma: shift must be 0 or 4");
-  const long nwin = (long)B * (H / WS) * (W / WS);
-  FEMASR_CHECK_ARG(nwin < (1l << 31), "window_attention_mma: too many windows");
-  // window groups: about two waves of the 7 resident CTAs per SM, so the tail stays short while a CTA still reuses
-  // its bias fragments for many windows
-  long groups = (long)sm_count() * FEMASR_ATTN_MINBLOCKS * 2 / heads;
-  if (groups < 1) groups = 1;
-  if (groups > nwin) groups = nwin;
-  window_attention_mma_kernel<<<(unsigned)(groups * heads), 128, 0, as_stream(stream)>>>(
-      qkv, bias_frag, out, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), H, W, C, heads, shift, (int)nwin);
+  const long blocks = (long)B * (H / WS) * (W / WS) * heads;
+  window_attention_mma_kernel<<<(unsigned)blocks, 128, 0, as_stream(stream)>>>(
+      qkv, bias_frag, out, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), H, W, C, heads, shift);
   return launch_status("window_attention_mma_kernel");
 }
 

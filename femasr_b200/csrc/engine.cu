@@ -739,7 +739,7 @@ static int check_geometry(femasr_net* net, int B, int H, int W) {
 }  // namespace femasr
 
 extern "C" const char* femasr_last_error(void) { return g_err.c_str(); }
-extern "C" int femasr_abi_version(void) { return 2; }
+extern "C" int femasr_abi_version(void) { return 3; }   // 3: + femasr_vq_match_tc / femasr_vq_finish / femasr_in_conv_im2col / femasr_in_conv_pad_weight
 
 extern "C" int femasr_device_cc(void) {
   int dev = 0;

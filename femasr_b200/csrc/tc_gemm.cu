@@ -1306,9 +1306,14 @@ static TilePlan plan_tiles(const femasr_tc_args* a, int H, int W) {
   // three or more column tiles (qkv) also gain 5 % paired; fc1 (GELU + split epilogue, issue-bound) and proj do not.
   const bool wide_plain_linear = a->ksize == 1 && a->act == FEMASR_ACT_NONE && a->y && a->Cout >= 768;
   t.pair = pair_req >= 0 ? pair_req != 0 : (t.BN == 256 && ((long)taps * a->Cin >= 1024 || wide_plain_linear));
-  // K-sliced linears (fc2 in front of the VQ): 128-wide unpaired tiles - the accumulator drain of a slice is half as
-  // long and twice as many tiles overlap it (0.210 -> 0.197 ms)
-  if (bn_env == 0 && a->ksize == 1 && a->slice_kb > 0 && t.BN == 256 && pair_req < 0) { t.BN = 128; t.pair = false; }
+  // K-sliced layers (in front of the VQ): 128-wide tiles - the accumulator drain of a slice is half as long, twice as
+  // many tiles overlap it (fc2 0.210 -> 0.197 ms),
+  // and with 128-wide tiles the three-buffer protocol applies (the MMA no longer waits for the fold): fc2 0.213 -> 0.181,
+  // 256 -> 256 @64² sliced conv 0.367 -> 0.319 ms paired (profiles/sweep_bn_pair_r2.txt)
+  if (bn_env == 0 && a->slice_kb > 0 && t.BN == 256 && pair_req < 0) {
+    t.BN = 128;
+    t.pair = a->ksize == 3 && (long)taps * a->Cin >= 1024;
+  }
   // strip mode (one activation strip shared by the three horizontal taps): a->strip 1/0/-1 like pair
   static const int strip_env = [] { const char* e = getenv("FEMASR_TC_STRIP"); return e ? atoi(e) : -1; }();
   const int strip_req = a->strip >= 0 ? a->strip : strip_env;
