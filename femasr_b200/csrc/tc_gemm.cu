@@ -109,6 +109,13 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }          // writes complete
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-serialisation attribute may start (its CTAs
+// become resident as the predecessor's retire, it runs its prologue) before the predecessor has finished;
+// griddepcontrol.wait blocks until the predecessor grid has completed and its memory is visible.  Both are no-ops in a
+// plain launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // One lane of a converged warp (elect.sync).  The single-thread roles (TMA producer, MMA issuer) are entered through this
 // instead of `lane == 0`: with a data-dependent lane test ptxas must assume several lanes with different operands may be
 // active and wraps EVERY UTCHMMA / UTMALDG in an ELECT ... BRA.U.ANY serialisation loop with R2UR moves (~10 SASS
@@ -387,6 +394,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();        // the next kernel of the stream may begin its own prologue as our CTAs retire
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::NBAR_PIPE; ++s) mbar_init(bar_base + 8u * s, 1);
     // tmem-empty: ONE arrival per epilogue warp (of both CTAs when paired), by an elected lane after __syncwarp - 512
@@ -409,6 +417,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  pdl_wait();                     // barriers initialised, TMEM allocated: from here on the predecessor's output is read
 
   const int ksz = p.taps == 9 ? 3 : 1;   // (p.up: taps == 4, offsets from the phase)
 
@@ -1059,6 +1068,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256) tc_prepare_flat_kernel(const float4* __restrict__ x, uint2* __restrict__ hi,
                                                               uint2* __restrict__ lo, const float* __restrict__ sc,
                                                               const float* __restrict__ sh, int C, int per_image4) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const long base = (long)b * per_image4;
   const int i0 = blockIdx.x * (256 * PREP_U) + threadIdx.x;
@@ -1102,6 +1113,8 @@ __global__ void __launch_bounds__(256) tc_prepare_flat_kernel(const float4* __re
 __global__ void __launch_bounds__(256) tc_prepare_ln_kernel(const float* __restrict__ x, __half* __restrict__ hi,
                                                             __half* __restrict__ lo, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, long M, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -1219,6 +1232,36 @@ static int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t*
   return FEMASR_OK;
 }
 
+// Launch with the programmatic-stream-serialisation attribute when FEMASR_PDL=1.  Only kernels that execute
+// griddepcontrol.wait before their first dependent global access are launched this way.  OFF by default: measured on
+// the whole step (same box, CUDA-graph replay, profiles/bench_r2_pdl_ab.json) 78.5 ms without, 81.3 ms with it - the
+// persistent 227 KB CTAs cannot become resident before the predecessor's retire anyway, so only the (already short)
+// launch gap is exposed to overlap, and the early-launched grids cost more than that saves.
+static bool pdl_enabled() {
+  static const int env = [] { const char* e = getenv("FEMASR_PDL"); return e ? atoi(e) : 0; }();
+  return env != 0;
+}
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // output maps of the TMA-store epilogue (valid when p.tma_out != 0; otherwise copies of an input map, never dereferenced)
 struct OutMaps { CUtensorMap y, oh, ol; };
 
@@ -1233,20 +1276,16 @@ static int launch_tc_v(const CUtensorMap& ah, const CUtensorMap& al, const CUten
   }
   if constexpr (!PAIR) {
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    tc_igemm_kernel<BN, false, STRIP, BRES, RES><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, om.y, om.oh, om.ol, p);
+    FEMASR_CUDA(launch_pdl(tc_igemm_kernel<BN, false, STRIP, BRES, RES>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, 1,
+                           ah, al, bh, bl, om.y, om.oh, om.ol, p));
     return launch_status("tc_igemm_kernel");
   } else {
     const int num_m = p.num_tiles / p.n_tiles;
     const int phases = p.up ? 4 : 1;
     const int work = phases * ((num_m / phases + 1) / 2) * p.n_tiles;
     const int pairs = work < sm_count() / 2 ? work : sm_count() / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    FEMASR_CUDA(cudaLaunchKernelEx(&cfg, tc_igemm_kernel<BN, true, false, false, RES>, ah, al, bh, bl, om.y, om.oh, om.ol, p));
+    FEMASR_CUDA(launch_pdl(tc_igemm_kernel<BN, true, false, false, RES>, dim3(2 * pairs), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, 2,
+                           ah, al, bh, bl, om.y, om.oh, om.ol, p));
     return launch_status("tc_igemm_kernel(pair)");
   }
 }
@@ -1269,7 +1308,8 @@ static int launch_vq(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
   }
   const int num_m = p.num_tiles / p.n_tiles;
   const int grid = num_m < sm_count() ? num_m : sm_count();
-  tc_igemm_kernel<BN, false, false, false, false, true><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, ah, ah, ah, p);
+  FEMASR_CUDA(launch_pdl(tc_igemm_kernel<BN, false, false, false, false, true>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, 1,
+                         ah, al, bh, bl, ah, ah, ah, p));
   return launch_status("tc_igemm_kernel(vq)");
 }
 
@@ -1387,7 +1427,7 @@ extern "C" int femasr_tc_prepare(const float* x, void* a_hi, void* a_lo, int mod
   if (mode == FEMASR_PRO_LN) {
     FEMASR_CHECK_ARG(C == 256 && gamma && beta && !upsample, "tc_prepare: LN mode needs C=256, gamma/beta, no upsample");
     const long M = (long)B * H * W;
-    tc_prepare_ln_kernel<<<(unsigned)cdiv(M, 8), 256, 0, st>>>(x, hi, lo, gamma, beta, M, eps);
+    FEMASR_CUDA(launch_pdl(tc_prepare_ln_kernel, dim3((unsigned)cdiv(M, 8)), dim3(256), 0, st, 1, x, hi, lo, gamma, beta, M, eps));
     return launch_status("tc_prepare_ln_kernel");
   }
   static const int flat_env = [] { const char* e = getenv("FEMASR_PREP_FLAT"); return e ? atoi(e) : 1; }();
@@ -1398,12 +1438,12 @@ extern "C" int femasr_tc_prepare(const float* x, void* a_hi, void* a_lo, int mod
     const float4* x4 = reinterpret_cast<const float4*>(x);
     if (mode == FEMASR_PRO_GN_SILU) {
       FEMASR_CHECK_ARG(pro_a && pro_b, "tc_prepare: GN mode needs the scale/shift tables");
-      tc_prepare_flat_kernel<FEMASR_PRO_GN_SILU><<<grid, 256, 0, st>>>(x4, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), pro_a, pro_b, C, per4);
+      FEMASR_CUDA(launch_pdl(tc_prepare_flat_kernel<FEMASR_PRO_GN_SILU>, grid, dim3(256), 0, st, 1, x4, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), pro_a, pro_b, C, per4));
     } else if (mode == FEMASR_PRO_GN_SILU_FAST) {
       FEMASR_CHECK_ARG(pro_a && pro_b, "tc_prepare: GN mode needs the scale/shift tables");
-      tc_prepare_flat_kernel<FEMASR_PRO_GN_SILU_FAST><<<grid, 256, 0, st>>>(x4, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), pro_a, pro_b, C, per4);
+      FEMASR_CUDA(launch_pdl(tc_prepare_flat_kernel<FEMASR_PRO_GN_SILU_FAST>, grid, dim3(256), 0, st, 1, x4, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), pro_a, pro_b, C, per4));
     } else {
-      tc_prepare_flat_kernel<FEMASR_PRO_NONE><<<grid, 256, 0, st>>>(x4, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), nullptr, nullptr, C, per4);
+      FEMASR_CUDA(launch_pdl(tc_prepare_flat_kernel<FEMASR_PRO_NONE>, grid, dim3(256), 0, st, 1, x4, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), (const float*)nullptr, (const float*)nullptr, C, per4));
     }
     return launch_status("tc_prepare_flat_kernel");
   }
