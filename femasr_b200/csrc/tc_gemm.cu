@@ -234,7 +234,10 @@ constexpr int TC_BM = 128, TC_BK = 64;
 // epilogue warps per TMEM lane quarter (= column split of the accumulator): 4 (16 epilogue warps) for the 128/256-wide
 // tiles - measured +4 % end to end over 8 warps, the short-K layers are epilogue-issue bound - but 2 for the 64-wide
 // tiles, where a warp would own a single 16-column chunk and the per-tile fixed work dominates (measured -15 %).
-constexpr int nsplit_for(int BN) { return BN == 64 ? 2 : 4; }
+#ifndef FEMASR_NSPLIT_WIDE
+#define FEMASR_NSPLIT_WIDE 4      // study knob: 2 = 8 epilogue warps with 168 registers each for the 128 / 256-wide tiles
+#endif
+constexpr int nsplit_for(int BN) { return BN == 64 ? 2 : FEMASR_NSPLIT_WIDE; }
 constexpr int tc_threads_for(int BN) { return 128 + 32 * 4 * nsplit_for(BN); }
 constexpr int A_PLANE_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 
@@ -841,7 +844,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         // 64-wide tiles (8 epilogue warps, registers to spare): the NEXT chunk's TMEM load is already in flight while this
         // chunk goes through its transpose / math / store phases (the exposed tcgen05.ld latency was 9 % of the 64 -> 64
         // conv's samples); the wide tiles sit at the 96-register cap of a 640-thread CTA and load on demand.
-        constexpr bool PIPE_LD = BN == 64;
+        constexpr bool PIPE_LD = Cfg::NSPLIT == 2;         // 8 epilogue warps: up to 168 registers per thread
         uint32_t r[16];
         if (PIPE_LD && nslices == 1) {
           if (ci == 0) tmem_ld16_async(t_row, rn);

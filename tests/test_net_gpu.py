@@ -194,3 +194,20 @@ def test_out_of_range_indices_raise(cuda):
         net.decode_indices(bad)
     with pytest.raises(FemasrError, match="out of range"):
         net(torch.rand(1, 3, 32, 32, device=cuda), [torch.full((1, 1, 16, 16), -1, dtype=torch.int64, device=cuda)])
+
+
+def test_two_devices_in_one_process(cuda):
+    """The reference surface is `.to(any device)`: two engines on two GPUs of one process must both work (kernel
+    attributes / SM counts are per device).  Needs a 2-GPU box; skipped otherwise."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sd = random_state_dict(4, 256, seed=44, init="perturbed")
+    x = torch.rand(1, 3, 32, 128, generator=torch.Generator().manual_seed(45))
+    outs = []
+    for dev in (torch.device("cuda", 1), torch.device("cuda", 0), torch.device("cuda", 1)):
+        net = make_net(4, 256, sd, dev, gemm_path=1)
+        out, _, _, idx = net(x.to(dev))
+        outs.append((out.cpu(), idx[0].cpu()))
+        assert out.device == dev
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][0], outs[2][0])
