@@ -202,6 +202,22 @@ class FeMaSRNet(nn.Module):
         the device - img2tensor, /255, test() padding and crop, tensor2img (inference_femasr.py:54-64)."""
         return self._native(images.device).sr_uint8(images)
 
+    @torch.no_grad()
+    def encode_codes(self, input):
+        """Extension: the codebook indices of `input` in the compact wire format (femasr_b200/wire.py: ceil(log2 n_e) bits
+        per code, packed on the device) -> (uint8 stream, index-map shape [B,1,h,w]).  Single-codebook nets."""
+        from femasr_b200.wire import pack_codes
+        idx = self.encode_and_decode(input)[3]
+        if len(idx) != 1:
+            raise NotImplementedError("encode_codes: single-codebook networks only")
+        return pack_codes(idx[0], self.n_e), tuple(idx[0].shape)
+
+    @torch.no_grad()
+    def decode_codes(self, packed, shape):
+        """Extension: inverse of encode_codes - unpack on the device and run decode_indices (femasr_arch.py:376-385)."""
+        from femasr_b200.wire import unpack_codes
+        return self.decode_indices(unpack_codes(packed, tuple(shape), self.n_e))
+
     def forward(self, input, gt_indices=None):
         """femasr_arch.py:470-479."""
         return self.encode_and_decode(input, gt_indices)

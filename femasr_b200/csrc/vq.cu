@@ -170,6 +170,55 @@ __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict_
   if (lane == 0 && loss_rows) loss_rows[r] = l;
 }
 
+// Compact wire format of index maps (femasr_b200/wire.py): `bits` = ceil(log2 n_e) bits per code, little-endian bit
+// stream (code i occupies bits [i*bits, (i+1)*bits), least significant bit first).  Eight codes are exactly `bits`
+// bytes, so one thread packs / unpacks one group of eight through a 128-bit shift register.  bits <= 16.
+__global__ void __launch_bounds__(256) pack_codes_kernel(const int64_t* __restrict__ idx, uint8_t* __restrict__ out,
+                                                         long n, int bits, int n_e, int* __restrict__ bad) {
+  const long g = (long)blockIdx.x * 256 + threadIdx.x;
+  if (g * 8 >= n) return;
+  unsigned long long lo = 0ull, hi = 0ull;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const long i = g * 8 + k;
+    long v = i < n ? idx[i] : 0;
+    if (v < 0 || v >= n_e) { atomicExch(bad, 1); v = 0; }
+    const int sh = k * bits;
+    const unsigned long long u = (unsigned long long)v;
+    if (sh < 64) { lo |= u << sh; if (sh + bits > 64) hi |= u >> (64 - sh); }
+    else hi |= u << (sh - 64);
+  }
+  const long total = (n * bits + 7) / 8;
+  for (int b = 0; b < bits; ++b) {
+    const long o = g * bits + b;
+    if (o < total) out[o] = (uint8_t)(b < 8 ? (lo >> (8 * b)) : (hi >> (8 * (b - 8))));
+  }
+}
+
+__global__ void __launch_bounds__(256) unpack_codes_kernel(const uint8_t* __restrict__ in, int64_t* __restrict__ idx, long n,
+                                                           int bits) {
+  const long g = (long)blockIdx.x * 256 + threadIdx.x;
+  if (g * 8 >= n) return;
+  const long total = (n * bits + 7) / 8;
+  unsigned long long lo = 0ull, hi = 0ull;
+  for (int b = 0; b < bits; ++b) {
+    const long o = g * bits + b;
+    const unsigned long long v = o < total ? in[o] : 0;
+    if (b < 8) lo |= v << (8 * b); else hi |= v << (8 * (b - 8));
+  }
+  const unsigned long long mask = (1ull << bits) - 1ull;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const long i = g * 8 + k;
+    if (i >= n) break;
+    const int sh = k * bits;
+    unsigned long long u;
+    if (sh < 64) { u = lo >> sh; if (sh + bits > 64) u |= hi << (64 - sh); }
+    else u = hi >> (sh - 64);
+    idx[i] = (int64_t)(u & mask);
+  }
+}
+
 template <bool ACC>
 __global__ void __launch_bounds__(1024) sum_scaled_kernel(const float* __restrict__ x, float* __restrict__ out, size_t n,
                                                           double scale) {
@@ -313,6 +362,33 @@ extern "C" int femasr_vq_finish(const float* z, const float* a, const void* cand
   vq_finish_kernel<<<(unsigned)cdiv(N, 8), 256, 0, as_stream(stream)>>>(z, a, reinterpret_cast<const uint2*>(cand), codebook, esq,
                                                                         idx, zq, loss_rows, stats, N, n_e, e_dim);
   return launch_status("vq_finish_kernel");
+}
+
+static int code_bits_of(int n_e) { int b = 0; while ((1l << b) < n_e) ++b; return b < 1 ? 1 : b; }
+
+extern "C" size_t femasr_packed_code_bytes(size_t numel, int n_e) {
+  return n_e < 2 ? 0 : (numel * (size_t)code_bits_of(n_e) + 7) / 8;
+}
+
+// status: device int set to 1 when a code lies outside [0, n_e) (the caller checks it; such codes are packed as 0)
+extern "C" int femasr_pack_codes(const int64_t* indices, void* packed, size_t numel, int n_e, int* status, void* stream) {
+  FEMASR_CHECK_ARG(indices && packed && status && numel > 0, "pack_codes: bad argument");
+  FEMASR_CHECK_ARG(n_e >= 2 && n_e <= 65536, "pack_codes: n_e must be in [2, 65536]");
+  cudaStream_t st = as_stream(stream);
+  FEMASR_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+  const long groups = (long)cdiv((long)numel, 8);
+  pack_codes_kernel<<<(unsigned)cdiv(groups, 256), 256, 0, st>>>(indices, reinterpret_cast<uint8_t*>(packed), (long)numel,
+                                                                code_bits_of(n_e), n_e, status);
+  return launch_status("pack_codes_kernel");
+}
+
+extern "C" int femasr_unpack_codes(const void* packed, int64_t* indices, size_t numel, int n_e, void* stream) {
+  FEMASR_CHECK_ARG(indices && packed && numel > 0, "unpack_codes: bad argument");
+  FEMASR_CHECK_ARG(n_e >= 2 && n_e <= 65536, "unpack_codes: n_e must be in [2, 65536]");
+  const long groups = (long)cdiv((long)numel, 8);
+  unpack_codes_kernel<<<(unsigned)cdiv(groups, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed),
+                                                                                   indices, (long)numel, code_bits_of(n_e));
+  return launch_status("unpack_codes_kernel");
 }
 
 extern "C" int femasr_sum_scaled(const float* x, float* out, size_t n, double scale, void* stream) {

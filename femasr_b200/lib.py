@@ -96,6 +96,9 @@ SIGNATURES = {
     "femasr_vq_select": (_I, [_V, _V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _V]),
     "femasr_vq_match_tc": (_I, [_V, _V, _V, _V, _V, _V, _I, _I, _I, _V]),
     "femasr_vq_finish": (_I, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _I, _I, _I, _V]),
+    "femasr_packed_code_bytes": (_Z, [_Z, _I]),
+    "femasr_pack_codes": (_I, [_V, _V, _Z, _I, _V, _V]),
+    "femasr_unpack_codes": (_I, [_V, _V, _Z, _I, _V]),
     "femasr_sum_scaled": (_I, [_V, _V, _Z, _D, _V]),
     "femasr_sum_scaled_add": (_I, [_V, _V, _Z, _D, _V]),
     "femasr_concat_channels": (_I, [_V, _I, _V, _I, _I, _I, _V, _I, _I, _I, _V]),

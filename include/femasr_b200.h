@@ -268,6 +268,12 @@ int femasr_vq_match_tc(const void* z_hi, const void* z_lo, const void* cb_blob, 
 int femasr_vq_finish(const float* z, const float* a, const void* cand, const float* codebook, const float* esq,
                      int64_t* idx, float* zq, float* loss_rows, unsigned int* stats, int N, int n_e, int e_dim,
                      void* stream);
+/* Compact wire format of codebook-index maps (extension; the reference moves int64 maps, femasr_arch.py:100,376-385):
+ * ceil(log2 n_e) bits per code, little-endian bit stream.  femasr_packed_code_bytes gives the stream length;
+ * *status (device int) becomes 1 if a code lies outside [0, n_e). */
+size_t femasr_packed_code_bytes(size_t numel, int n_e);
+int femasr_pack_codes(const int64_t* indices, void* packed, size_t numel, int n_e, int* status, void* stream);
+int femasr_unpack_codes(const void* packed, int64_t* indices, size_t numel, int n_e, void* stream);
 /* out[0] = scale * sum(x[0..n)) accumulated in double in a fixed order. */
 int femasr_sum_scaled(const float* x, float* out, size_t n, double scale, void* stream);
 /* out[0] += scale * sum(x[0..n)) (the running sum over codebooks, femasr_arch.py:371). */

@@ -49,21 +49,30 @@ def main(argv=None):
         imwrite(img, os.path.join(a.output, f"{name}{a.suffix}{ext}"))
 
     if a.batch > 0 and dev.type == "cuda":
+        import numpy as np
+        # same-shape buckets are flushed as soon as they hold `batch` images: at most (#distinct shapes x batch) decoded
+        # images are alive at any time, instead of the whole folder
         buckets, rest = {}, []
+
+        def flush(items):
+            batch = torch.from_numpy(np.stack([im for _, im in items])).to(dev)
+            for (path, _), o in zip(items, net.sr_uint8(batch).cpu().numpy()):
+                save(path, o)
+
         for path in paths:
             img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
             if img is not None and img.ndim == 3 and img.shape[2] == 3 and img.dtype == "uint8" and \
                     img.shape[0] * img.shape[1] < a.max_size ** 2:
-                buckets.setdefault(img.shape[:2], []).append((path, img))
+                items = buckets.setdefault(img.shape[:2], [])
+                items.append((path, img))
+                if len(items) == a.batch:
+                    flush(items)
+                    buckets[img.shape[:2]] = []
             else:
                 rest.append(path)
         for items in buckets.values():
-            for i in range(0, len(items), a.batch):
-                chunk = items[i:i + a.batch]
-                batch = torch.from_numpy(__import__("numpy").stack([im for _, im in chunk])).to(dev)
-                out = net.sr_uint8(batch).cpu().numpy()
-                for (path, _), o in zip(chunk, out):
-                    save(path, o)
+            if items:
+                flush(items)
         paths = rest
     for path in paths:
         img = cv2.imread(path, cv2.IMREAD_UNCHANGED)

@@ -211,3 +211,24 @@ def test_two_devices_in_one_process(cuda):
         assert out.device == dev
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert torch.equal(outs[0][0], outs[2][0])
+
+
+def test_compact_codes_on_the_device(cuda):
+    """encode_codes / decode_codes: the device pack / unpack kernels produce the same stream as the CPU tensor arithmetic
+    of femasr_b200/wire.py, and decoding the packed codes equals decode_indices on the index map."""
+    from femasr_b200.wire import pack_codes, packed_nbytes, unpack_codes
+    sd = random_state_dict(4, 256, seed=46, init="perturbed")
+    net = make_net(4, 256, sd, cuda, gemm_path=1)
+    x = torch.rand(2, 3, 32, 48, generator=torch.Generator().manual_seed(47)).to(cuda)
+    packed, shape = net.encode_codes(x)
+    idx = net(x)[3][0]
+    assert packed.is_cuda and packed.dtype == torch.uint8 and packed.numel() == packed_nbytes(idx.numel(), 1024) and shape == tuple(idx.shape)
+    assert torch.equal(packed.cpu(), pack_codes(idx.cpu(), 1024))
+    assert torch.equal(unpack_codes(packed, shape, 1024), idx)
+    assert torch.equal(net.decode_codes(packed, shape), net.decode_indices(idx))
+    for n_e, n in ((1000, 77), (2, 9), (65536, 64), (512, 4096)):       # odd widths, ragged tails
+        codes = torch.randint(0, n_e, (n,), generator=torch.Generator().manual_seed(n)).to(cuda)
+        p = pack_codes(codes, n_e)
+        assert torch.equal(p.cpu(), pack_codes(codes.cpu(), n_e)) and torch.equal(unpack_codes(p, (n,), n_e), codes)
+    with pytest.raises(ValueError):
+        pack_codes(torch.tensor([0, 1024], device=cuda), 1024)
