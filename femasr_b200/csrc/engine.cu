@@ -99,6 +99,7 @@ struct femasr_net {
   std::map<std::string, DevBuf> packed_mma;   // rel-pos bias in the mma attention kernel's fragment order
   std::map<std::string, DevBuf> tcw;      // tensor-core operand (split fp16), gemm_path 1
   std::map<std::string, DevBuf> tcw_up;   // sub-pixel phase filters of the upsample-fused 3x3 convs
+  std::map<std::string, DevBuf> tcw8, tcw_up8;   // the same two in the F8 cross-term packing (layers behind the VQ)
   std::map<std::string, DevBuf> esq;      // sum e^2 per codebook row, keyed by the codebook's parameter name
   struct Codebook { int scale, n_e, e_dim; };
   std::vector<Codebook> cbs;              // codebook_params rows; cbs[0].scale == 32
@@ -109,6 +110,7 @@ struct femasr_net {
   bool profile = false;
   bool tc_precise = true;                 // K-sliced fp32 accumulation for the layers in front of the VQ
   bool oc_mma = true;                     // out_conv on mma.sync in the tensor-core path (FEMASR_OUTCONV_MMA=0: SIMT kernel)
+  bool f8_cross = true;                   // layers behind the VQ: the two cross products of the split as one fp8 product (FEMASR_F8_CROSS=0: three fp16 products)
   bool in_conv_tc = true;                 // in_conv as an im2col GEMM on the tensor cores (FEMASR_IN_CONV_TC=0: fp32 SIMT kernel)
   int tc_slice_kb = 4;                    // K-slice length in 64-wide k-blocks (FEMASR_TC_SLICE_KB; study knob)
   bool vq_fused = true;                   // VQ distances on the tensor cores with the argmin fused (FEMASR_VQ_FUSED=0: fp32 SIMT z.E^T + vq_select)
@@ -122,6 +124,8 @@ struct femasr_net {
     for (auto& kv : packed_mma) cudaFree(kv.second.p);
     for (auto& kv : tcw) cudaFree(kv.second.p);
     for (auto& kv : tcw_up) cudaFree(kv.second.p);
+    for (auto& kv : tcw8) cudaFree(kv.second.p);
+    for (auto& kv : tcw_up8) cudaFree(kv.second.p);
     for (auto& kv : esq) cudaFree(kv.second.p);
   }
 };
@@ -305,19 +309,25 @@ struct Ctx {
       alo = ar.alloc((plane_halves + 1) / 2);
     }
     if (!dry() && ok()) {
+      // behind the VQ (bar: 1e-3 on the output): approximate-unit SiLU, and the two cross products of the split as one
+      // fp8 product (F8 mode: staging writes the interleaved e4m3 plane, the weights come from the F8 packing)
+      const bool relaxed = !precise && !precise_region;
+      const bool f8 = relaxed && net->f8_cross && !pre_hi && ksize == 3 && prologue != FEMASR_PRO_LN &&
+                      (upsample ? net->tcw_up8.count(wname + ".weight") : net->tcw8.count(wname + ".weight")) != 0;
       if (!pre_hi) {
-        // behind the VQ (bar: 1e-3 on the output) the SiLU uses the approximate exp/reciprocal units
-        const int pmode = (prologue == FEMASR_PRO_GN_SILU && !precise && !precise_region && net->fast_silu)
-                              ? FEMASR_PRO_GN_SILU_FAST : prologue;
-        run(detail_name("tc_prepare", pmode, Cin, Cin, Hin, Win, 0, 1, 0), 0.0, [&] {
-          return femasr_tc_prepare(x, ahi, alo, pmode, pa, pb, gamma, beta, B, Hin, Win, Cin, 0,
-                                   prologue == FEMASR_PRO_LN ? 1e-5f : 1e-6f, st);
+        const int pmode = (prologue == FEMASR_PRO_GN_SILU && relaxed && net->fast_silu) ? FEMASR_PRO_GN_SILU_FAST : prologue;
+        run(detail_name(f8 ? "tc_prepare_f8" : "tc_prepare", pmode, Cin, Cin, Hin, Win, 0, 1, 0), 0.0, [&] {
+          return f8 ? femasr_tc_prepare_f8(x, ahi, alo, pmode, pa, pb, B, Hin, Win, Cin, st)
+                    : femasr_tc_prepare(x, ahi, alo, pmode, pa, pb, gamma, beta, B, Hin, Win, Cin, 0,
+                                        prologue == FEMASR_PRO_LN ? 1e-5f : 1e-6f, st);
         });
       }
       femasr_tc_args t;
       memset(&t, 0, sizeof(t));
       t.a_hi = pre_hi ? pre_hi : ahi; t.a_lo = pre_hi ? pre_lo : alo;
-      t.w_blob = upsample ? net->tcw_up[wname + ".weight"].p : net->tcw[wname + ".weight"].p;
+      t.f8 = f8 ? 1 : 0;
+      t.w_blob = f8 ? (upsample ? net->tcw_up8[wname + ".weight"].p : net->tcw8[wname + ".weight"].p)
+                    : (upsample ? net->tcw_up[wname + ".weight"].p : net->tcw[wname + ".weight"].p);
       t.bias = P(wname + ".bias");
       t.res1 = res1; t.res2 = res2; t.y = y; t.out_hi = out_hi; t.out_lo = out_lo; t.gn_partial = gn_partial;
       t.B = B; t.H = Hin; t.W = Win; t.Cin = Cin; t.Cout = Cout; t.ksize = ksize; t.act = act; t.upsample = upsample;
@@ -739,7 +749,7 @@ static int check_geometry(femasr_net* net, int B, int H, int W) {
 }  // namespace femasr
 
 extern "C" const char* femasr_last_error(void) { return g_err.c_str(); }
-extern "C" int femasr_abi_version(void) { return 3; }   // 3: + femasr_vq_match_tc / femasr_vq_finish / femasr_in_conv_im2col / femasr_in_conv_pad_weight
+extern "C" int femasr_abi_version(void) { return 4; }   // 3: fused VQ + im2col in_conv entries; 4: femasr_tc_args.f8 + the F8 staging / packing entries
 
 extern "C" int femasr_device_cc(void) {
   int dev = 0;
@@ -784,6 +794,7 @@ extern "C" int femasr_net_create(const femasr_net_config* cfg, femasr_net** out)
   if (const char* ev = getenv("FEMASR_OUTCONV_MMA")) n->oc_mma = atoi(ev) != 0;
   if (const char* ev = getenv("FEMASR_VQ_FUSED")) n->vq_fused = atoi(ev) != 0;
   if (const char* ev = getenv("FEMASR_IN_CONV_TC")) n->in_conv_tc = atoi(ev) != 0;
+  if (const char* ev = getenv("FEMASR_F8_CROSS")) n->f8_cross = atoi(ev) != 0;
   if (const char* ev = getenv("FEMASR_TC_SLICE_KB")) n->tc_slice_kb = std::max(1, atoi(ev));
   build_spec(n);
   *out = n;
@@ -828,6 +839,12 @@ extern "C" int femasr_net_set_param(femasr_net* net, const char* name, const flo
       if (!tb.p) { FEMASR_CUDA(cudaMalloc(&tb.p, bytes)); tb.n = bytes / sizeof(float); }
       s = femasr_tc_pack_weight(rb.p, tb.p, pi.Cout, pi.Cin, pi.k, pi.k, st);
       if (s) return s;
+      if (net->f8_cross && pi.k == 3) {      // a 3x3 conv may run behind the VQ: keep the F8 packing next to the fp16 one
+        DevBuf& t8 = net->tcw8[key];
+        if (!t8.p) { FEMASR_CUDA(cudaMalloc(&t8.p, bytes)); t8.n = bytes / sizeof(float); }
+        s = femasr_tc_pack_weight_f8(rb.p, t8.p, pi.Cout, pi.Cin, pi.k, pi.k, st);
+        if (s) return s;
+      }
       // the five nearest-x2 -> conv3x3 sites (femasr_arch.py:172-173, 202-203) also get sub-pixel phase filters
       const std::string up1 = "multiscale_encoder.blocks." + std::to_string(net->depth + 1) + ".1.weight";
       const std::string up2 = "multiscale_encoder.blocks." + std::to_string(net->depth + 2) + ".1.weight";
@@ -837,7 +854,11 @@ extern "C" int femasr_net_set_param(femasr_net* net, const char* name, const flo
         DevBuf& ub = net->tcw_up[key];
         const size_t ubytes = femasr_tc_weight_bytes(4 * pi.Cout, pi.Cin, 2, 2);
         if (!ub.p) { FEMASR_CUDA(cudaMalloc(&ub.p, ubytes)); ub.n = ubytes / sizeof(float); }
-        return femasr_tc_pack_weight_up2(rb.p, ub.p, pi.Cout, pi.Cin, st);
+        s = femasr_tc_pack_weight_up2(rb.p, ub.p, pi.Cout, pi.Cin, st);
+        if (s || !net->f8_cross) return s;
+        DevBuf& u8 = net->tcw_up8[key];
+        if (!u8.p) { FEMASR_CUDA(cudaMalloc(&u8.p, ubytes)); u8.n = ubytes / sizeof(float); }
+        return femasr_tc_pack_weight_up2_f8(rb.p, u8.p, pi.Cout, pi.Cin, st);
       }
       return FEMASR_OK;
     }

@@ -18,6 +18,7 @@
 //           + prefetched residual(s) -> coalesced fp32 NHWC (or split-fp16 plane) stores.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include <algorithm>
 #include <cstring>
@@ -139,6 +140,15 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+// kind::f8f6f4 with both operands e4m3 (instruction-descriptor format fields 0 / 0, K = 32 per instruction = the same
+// 32 bytes per k-step as kind::f16): the two CROSS products of the split scheme for the layers behind the VQ (F8 mode)
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -221,6 +231,9 @@ struct TcP {
   int slice_kb;                  // >0: in-kernel K slicing - every slice_kb k-blocks the accumulator is drained into an
                                  // fp32 running sum kept in the second TMEM buffer (round-to-nearest adds by the
                                  // epilogue warps), so the truncating MMA accumulator never runs longer than a slice
+  int f8;                        // F8 mode: the "lo" planes of both operands hold interleaved e4m3 bytes per 64-channel chunk
+                                 // (A: [a_lo * 2^12 | a_hi], B: [w_hi * 2^-12 | w_lo]); one K = 128 fp8 product per k-block
+                                 // replaces the two fp16 cross products
   int tma_out;                   // 1: fp32 y, 2: split fp16 planes leave through TMA stores of the epilogue's staging tile
   int box_w, box_w_shift;        // a warp's 32 accumulator rows as a box of box_w x (32 / box_w) output pixels
   // VQ mode (template VQ): the GEMM is z . E^T and the epilogue keeps, per feature row, the four smallest distances
@@ -336,6 +349,13 @@ __device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint6
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma2_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 // commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
@@ -537,8 +557,13 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k) {
                 const uint64_t ko = (uint64_t)((k * 32) >> 4);
-                umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, (kh | cc | kw | k) ? 1u : 0u);
-                umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                const uint32_t first = (kh | cc | kw | k) ? 1u : 0u;
+                if (p.f8) {
+                  umma_f8(d_tmem, a_lo + ko, b_lo + ko, idesc, first);         // sum a_lo8 w_hi8 + sum a_hi8 w_lo8
+                } else {
+                  umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+                  umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                }
                 umma_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
               }
               if (!BRES) {
@@ -641,12 +666,20 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             // small cross terms first, the dominant hi*hi product last
             const uint32_t first = (kb != kb0 || k != 0) ? 1u : 0u;
             if (PAIR) {
-              umma2_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
-              umma2_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+              if (p.f8) {
+                umma2_f8(d_tmem, a_lo + ko, b_lo + ko, idesc, first);
+              } else {
+                umma2_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+                umma2_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+              }
               umma2_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
             } else {
-              umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
-              umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+              if (p.f8) {
+                umma_f8(d_tmem, a_lo + ko, b_lo + ko, idesc, first);
+              } else {
+                umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+                umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+              }
               umma_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
             }
           }
@@ -1112,6 +1145,64 @@ __global__ void __launch_bounds__(256) tc_prepare_flat_kernel(const float4* __re
   }
 }
 
+// F8 staging (layers behind the VQ): the hi plane as above; the second plane holds, per pixel and 64-channel chunk, 128
+// bytes = [e4m3((v - hi) * 2^12) x 64 | e4m3(v) x 64] - the A operand of the single K = 128 fp8 MMA group that replaces
+// the two fp16 cross products (the weights carry [e4m3(w_hi * 2^-12) | e4m3(w_lo)] at the matching offsets).
+// Error budget: scripts/exp_fp8_cross.py, 1.2e-4 output max-abs for the whole post-VQ scope (bar 1e-3).
+constexpr float F8_LO_SCALE = 4096.0f;
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return lo | (hi << 16);
+}
+template <int MODE>
+__global__ void __launch_bounds__(256) tc_prepare_flat_f8_kernel(const float4* __restrict__ x, uint2* __restrict__ hi,
+                                                                 uint32_t* __restrict__ x8, const float* __restrict__ sc,
+                                                                 const float* __restrict__ sh, int C, int per_image4) {
+  const int b = blockIdx.y;
+  const long base = (long)b * per_image4;
+  const int i0 = blockIdx.x * (256 * PREP_U) + threadIdx.x;
+  const int c4 = C >> 2;
+  float4 v[PREP_U];
+#pragma unroll
+  for (int u = 0; u < PREP_U; ++u) {
+    const int i = i0 + u * 256;
+    if (i < per_image4) v[u] = __ldg(x + base + i);
+  }
+#pragma unroll
+  for (int u = 0; u < PREP_U; ++u) {
+    const int i = i0 + u * 256;
+    if (i >= per_image4) break;
+    float w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+    const int cq = i % c4;                     // float4 index inside the pixel
+    const int c = cq * 4;
+    if (MODE == FEMASR_PRO_GN_SILU || MODE == FEMASR_PRO_GN_SILU_FAST) {
+      const float4 s = __ldg(reinterpret_cast<const float4*>(sc + (long)b * C + c));
+      const float4 t = __ldg(reinterpret_cast<const float4*>(sh + (long)b * C + c));
+      const float ss[4] = {s.x, s.y, s.z, s.w}, tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float n = fmaf(w[k], ss[k], tt[k]);
+        w[k] = MODE == FEMASR_PRO_GN_SILU_FAST ? __fdividef(n, 1.0f + __expf(-n)) : silu_f(n);
+      }
+    }
+    __align__(8) __half h[4];
+    float l[4], cl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      cl[k] = fminf(fmaxf(w[k], -65504.f), 65504.f);
+      h[k] = __float2half_rn(cl[k]);
+      l[k] = (cl[k] - __half2float(h[k])) * F8_LO_SCALE;
+    }
+    hi[base + i] = *reinterpret_cast<const uint2*>(h);
+    // byte layout of the pixel's x8 row: chunk (c / 64) * 128 + (c % 64) for the lo part, + 64 for the hi part
+    const long pix = (base + i) / c4;
+    const long word = pix * (C >> 1) + (c >> 6) * 32 + ((c & 63) >> 2);
+    x8[word] = pack_e4m3x4(l[0], l[1], l[2], l[3]);
+    x8[word + 16] = pack_e4m3x4(cl[0], cl[1], cl[2], cl[3]);
+  }
+}
+
 // LayerNorm (C = 256, eps) fused with the split: one warp per token row.
 __global__ void __launch_bounds__(256) tc_prepare_ln_kernel(const float* __restrict__ x, __half* __restrict__ hi,
                                                             __half* __restrict__ lo, const float* __restrict__ gamma,
@@ -1178,6 +1269,34 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, __half* __res
   const __half h = __float2half_rn(v);
   hi[i] = h;
   lo[i] = __float2half_rn(v - __half2float(h));
+}
+
+// F8 variant of the packed weights: hi plane as above; the second plane holds per (row, 64-wide k chunk) 128 bytes =
+// [e4m3(w_hi * 2^-12) x 64 | e4m3(w_lo) x 64] (see tc_prepare_flat_f8_kernel)
+__global__ void tc_pack_weight_f8_kernel(const float* __restrict__ w, __half* __restrict__ hi, uint8_t* __restrict__ x8,
+                                         const unsigned int* __restrict__ absmax, float* __restrict__ inv_scale, int Cout,
+                                         int Cin, int KH, int KW) {
+  const float mx = __uint_as_float(*absmax);
+  int ex = 0;
+  if (mx > 0.f) frexpf(mx, &ex);
+  const int s = mx > 0.f ? 10 - ex : 0;
+  const float scale = ldexpf(1.0f, s);
+  const long n = (long)Cout * Cin * KH * KW;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *inv_scale = ldexpf(1.0f, -s);
+  if (i >= n) return;
+  const long K = (long)Cin * KH * KW;
+  const int co = (int)(i / K);
+  const long k = i - (long)co * K;
+  const int tap = (int)(k / Cin), ci = (int)(k - (long)tap * Cin);
+  const int kh = tap / KW, kw = tap - kh * KW;
+  const float v = w[(((long)co * Cin + ci) * KH + kh) * KW + kw] * scale;
+  const __half h = __float2half_rn(v);
+  hi[i] = h;
+  const float hf = __half2float(h);
+  uint8_t* row = x8 + (long)co * K * 2 + (k >> 6) * 128 + (k & 63);
+  row[0] = (uint8_t)__nv_cvt_float_to_fp8(hf * (1.0f / F8_LO_SCALE), __NV_SATFINITE, __NV_E4M3);
+  row[64] = (uint8_t)__nv_cvt_float_to_fp8(v - hf, __NV_SATFINITE, __NV_E4M3);
 }
 
 // nearest-x2 upsample followed by a 3x3 conv == four 2x2 convs on the low-res grid (one per output phase
@@ -1387,9 +1506,10 @@ extern "C" size_t femasr_tc_weight_bytes(int Cout, int Cin, int kh, int kw) {
   return (size_t)2 * Cout * Cin * kh * kw * sizeof(__half) + 256;   // hi plane, lo plane, then {absmax, inv_scale}
 }
 
-// Layout of the packed tensor-core weight blob: [hi plane][lo plane][uint absmax][float inv_scale] (see above).
-extern "C" int femasr_tc_pack_weight(const float* w_oihw, void* blob, int Cout, int Cin, int kh, int kw, void* stream) {
+// Layout of the packed tensor-core weight blob: [hi plane][lo plane | F8: interleaved e4m3 plane][uint absmax][float inv_scale].
+static int tc_pack_weight_impl(const float* w_oihw, void* blob, int Cout, int Cin, int kh, int kw, bool f8, void* stream) {
   FEMASR_CHECK_ARG(w_oihw && blob && Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "tc_pack_weight: bad argument");
+  FEMASR_CHECK_ARG(!f8 || Cin % 64 == 0, "tc_pack_weight_f8: Cin must be a multiple of 64");
   const long n = (long)Cout * Cin * kh * kw;
   __half* hi = reinterpret_cast<__half*>(blob);
   __half* lo = hi + n;
@@ -1400,13 +1520,23 @@ extern "C" int femasr_tc_pack_weight(const float* w_oihw, void* blob, int Cout, 
   absmax_kernel<<<(unsigned)std::min<long>(cdiv(n, 256), 1024), 256, 0, st>>>(w_oihw, amax, n);
   int s = launch_status("absmax_kernel");
   if (s) return s;
+  if (f8) {
+    tc_pack_weight_f8_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(w_oihw, hi, reinterpret_cast<uint8_t*>(lo), amax, inv, Cout, Cin, kh, kw);
+    return launch_status("tc_pack_weight_f8_kernel");
+  }
   tc_pack_weight_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(w_oihw, hi, lo, amax, inv, Cout, Cin, kh, kw);
   return launch_status("tc_pack_weight_kernel");
+}
+extern "C" int femasr_tc_pack_weight(const float* w_oihw, void* blob, int Cout, int Cin, int kh, int kw, void* stream) {
+  return tc_pack_weight_impl(w_oihw, blob, Cout, Cin, kh, kw, false, stream);
+}
+extern "C" int femasr_tc_pack_weight_f8(const float* w_oihw, void* blob, int Cout, int Cin, int kh, int kw, void* stream) {
+  return tc_pack_weight_impl(w_oihw, blob, Cout, Cin, kh, kw, true, stream);
 }
 
 // Packed phase filters for the fused upsample+conv: a blob like femasr_tc_pack_weight's for the stacked
 // [4*Cout][Cin][2][2] filter bank (femasr_tc_weight_bytes(4*Cout, Cin, 2, 2) bytes).
-extern "C" int femasr_tc_pack_weight_up2(const float* w_oihw, void* blob, int Cout, int Cin, void* stream) {
+static int tc_pack_weight_up2_impl(const float* w_oihw, void* blob, int Cout, int Cin, bool f8, void* stream) {
   FEMASR_CHECK_ARG(w_oihw && blob && Cout > 0 && Cin > 0, "tc_pack_weight_up2: bad argument");
   cudaStream_t st = as_stream(stream);
   float* tmp = nullptr;
@@ -1414,9 +1544,39 @@ extern "C" int femasr_tc_pack_weight_up2(const float* w_oihw, void* blob, int Co
   FEMASR_CUDA(cudaMallocAsync(&tmp, n * sizeof(float), st));
   subpixel_weights_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(w_oihw, tmp, Cout, Cin);
   int s = launch_status("subpixel_weights_kernel");
-  if (!s) s = femasr_tc_pack_weight(tmp, blob, 4 * Cout, Cin, 2, 2, stream);
+  if (!s) s = tc_pack_weight_impl(tmp, blob, 4 * Cout, Cin, 2, 2, f8, stream);
   cudaFreeAsync(tmp, st);
   return s;
+}
+extern "C" int femasr_tc_pack_weight_up2(const float* w_oihw, void* blob, int Cout, int Cin, void* stream) {
+  return tc_pack_weight_up2_impl(w_oihw, blob, Cout, Cin, false, stream);
+}
+extern "C" int femasr_tc_pack_weight_up2_f8(const float* w_oihw, void* blob, int Cout, int Cin, void* stream) {
+  return tc_pack_weight_up2_impl(w_oihw, blob, Cout, Cin, true, stream);
+}
+
+// F8 operand staging (see tc_prepare_flat_f8_kernel): modes NONE / GN_SILU / GN_SILU_FAST, no replication
+extern "C" int femasr_tc_prepare_f8(const float* x, void* a_hi, void* a_x8, int mode, const float* pro_a, const float* pro_b,
+                                    int B, int H, int W, int C, void* stream) {
+  FEMASR_CHECK_ARG(x && a_hi && a_x8 && B > 0 && H > 0 && W > 0, "tc_prepare_f8: bad argument");
+  FEMASR_CHECK_ARG(C % 64 == 0, "tc_prepare_f8: C must be a multiple of 64");
+  FEMASR_CHECK_ARG((long)H * W * (C / 4) < (1l << 30) && B <= 65535, "tc_prepare_f8: tensor too large for the flat kernel");
+  cudaStream_t st = as_stream(stream);
+  const int per4 = H * W * (C / 4);
+  const dim3 grid((unsigned)cdiv(per4, 256 * PREP_U), (unsigned)B);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  uint2* hi = reinterpret_cast<uint2*>(a_hi);
+  uint32_t* x8 = reinterpret_cast<uint32_t*>(a_x8);
+  if (mode == FEMASR_PRO_GN_SILU || mode == FEMASR_PRO_GN_SILU_FAST) {
+    FEMASR_CHECK_ARG(pro_a && pro_b, "tc_prepare_f8: GN mode needs the scale/shift tables");
+    if (mode == FEMASR_PRO_GN_SILU) tc_prepare_flat_f8_kernel<FEMASR_PRO_GN_SILU><<<grid, 256, 0, st>>>(x4, hi, x8, pro_a, pro_b, C, per4);
+    else tc_prepare_flat_f8_kernel<FEMASR_PRO_GN_SILU_FAST><<<grid, 256, 0, st>>>(x4, hi, x8, pro_a, pro_b, C, per4);
+  } else if (mode == FEMASR_PRO_NONE) {
+    tc_prepare_flat_f8_kernel<FEMASR_PRO_NONE><<<grid, 256, 0, st>>>(x4, hi, x8, nullptr, nullptr, C, per4);
+  } else {
+    return fail(FEMASR_ERR_ARG, "tc_prepare_f8: bad mode");
+  }
+  return launch_status("tc_prepare_flat_f8_kernel");
 }
 
 extern "C" int femasr_tc_prepare(const float* x, void* a_hi, void* a_lo, int mode, const float* pro_a, const float* pro_b,
@@ -1542,6 +1702,8 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
                    "tc_igemm: gn_partial needs a 3x3 conv with Cout in {64,128,256}");
   p.B = B; p.H = H; p.W = W; p.Cin = a->Cin; p.Cout = a->Cout; p.taps = taps; p.act = a->act;
   p.up = a->upsample ? 1 : 0; p.stride = stride;
+  p.f8 = a->f8 ? 1 : 0;
+  FEMASR_CHECK_ARG(!a->f8 || a->slice_kb == 0, "tc_igemm: the F8 cross-term mode is for the layers behind the VQ (no K slicing)");
   const TilePlan plan = plan_tiles(a, H, W);
   p.Wt = plan.Wt; p.Ht = plan.Ht; p.wt_shift = plan.wt_shift; p.tiles_x = plan.tiles_x; p.tiles_y = plan.tiles_y;
   const int BN = plan.BN;

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FEMASR_LIB") or os.path.join(_HERE, "libfemasr_b200.so")
 
 PRO_NONE, PRO_GN_SILU, PRO_LN, PRO_GN_SILU_FAST = 0, 1, 2, 3
-ABI_VERSION = 3          # femasr_abi_version() of the library this binding was written against (include/femasr_b200.h)
+ABI_VERSION = 4          # femasr_abi_version() of the library this binding was written against (include/femasr_b200.h)
 ACT_NONE, ACT_GELU = 0, 1
 TAP_STAGES = ("in_conv", "down", "swin", "up1", "up2", "z", "zq", "after_quant", "dec0", "dec1", "dec2")
 
@@ -49,7 +49,7 @@ class TcArgs(C.Structure):
                 ("ksize", C.c_int), ("act", C.c_int), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
                 ("stride", C.c_int), ("kb_begin", C.c_int), ("kb_count", C.c_int),
                 ("slice_kb", C.c_int), ("pair", C.c_int), ("strip", C.c_int), ("gn_partial", C.c_void_p),
-                ("upsample", C.c_int)]
+                ("upsample", C.c_int), ("f8", C.c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/femasr_b200.h declares
@@ -82,6 +82,9 @@ SIGNATURES = {
     "femasr_tc_pack_weight": (_I, [_V, _V, _I, _I, _I, _I, _V]),
     "femasr_tc_pack_weight_up2": (_I, [_V, _V, _I, _I, _V]),
     "femasr_tc_prepare": (_I, [_V, _V, _V, _I, _V, _V, _V, _V, _I, _I, _I, _I, _I, _F, _V]),
+    "femasr_tc_prepare_f8": (_I, [_V, _V, _V, _I, _V, _V, _I, _I, _I, _I, _V]),
+    "femasr_tc_pack_weight_f8": (_I, [_V, _V, _I, _I, _I, _I, _V]),
+    "femasr_tc_pack_weight_up2_f8": (_I, [_V, _V, _I, _I, _V]),
     "femasr_tc_igemm": (_I, [C.POINTER(TcArgs), _V]),
     "femasr_tc_gn_partial_rows": (_I, [C.POINTER(TcArgs)]),
     "femasr_gn_finalize_rows": (_I, [_V, _V, _V, _V, _V, _I, _I, _I, _I, _F, _V]),

@@ -202,6 +202,10 @@ typedef struct {
                               rows = femasr_tc_gn_partial_rows(args); finished by femasr_gn_finalize_rows */
   int upsample;            /* 1: y [B,2H,2W,Cout] = conv3x3(nearest_x2(a)), evaluated as 4 sub-pixel 2x2 convs on the
                               low-res grid; a_* are at the LOW resolution and w_blob comes from femasr_tc_pack_weight_up2 */
+  int f8;                  /* 1: F8 cross-term mode (layers behind the VQ, error budget 1e-3 on the output): a_lo and the
+                              blob's second plane hold interleaved e4m3 bytes (femasr_tc_prepare_f8 /
+                              femasr_tc_pack_weight_f8) and the two cross products a_lo*w_hi + a_hi*w_lo run as ONE
+                              kind::f8f6f4 product at twice the fp16 rate: 2.0 instead of 3.0 MMA units per k-step */
 } femasr_tc_args;
 size_t femasr_tc_weight_bytes(int Cout, int Cin, int kh, int kw);
 int femasr_tc_pack_weight(const float* w_oihw, void* blob, int Cout, int Cin, int kh, int kw, void* stream);
@@ -212,6 +216,12 @@ int femasr_tc_pack_weight_up2(const float* w_oihw_3x3, void* blob, int Cout, int
 int femasr_tc_prepare(const float* x, void* a_hi, void* a_lo, int mode, const float* pro_a, const float* pro_b,
                       const float* gamma, const float* beta, int B, int H, int W, int C, int upsample,
                       float eps, void* stream);
+/* F8 cross-term mode (femasr_tc_args.f8): per 64-channel chunk the second operand plane holds 128 bytes
+ * [e4m3(lo * 2^12) x 64 | e4m3(value) x 64] (activations) resp. [e4m3(w_hi * 2^-12) x 64 | e4m3(w_lo) x 64] (weights). */
+int femasr_tc_prepare_f8(const float* x, void* a_hi, void* a_x8, int mode, const float* pro_a, const float* pro_b,
+                         int B, int H, int W, int C, void* stream);
+int femasr_tc_pack_weight_f8(const float* w_oihw, void* blob, int Cout, int Cin, int kh, int kw, void* stream);
+int femasr_tc_pack_weight_up2_f8(const float* w_oihw_3x3, void* blob, int Cout, int Cin, void* stream);
 int femasr_tc_igemm(const femasr_tc_args* a, void* stream);
 /* number of GroupNorm partial rows per image femasr_tc_igemm will write for these arguments (the tiling is
  * chosen from the shape / flags; pointers in `a` are not read) */

@@ -28,6 +28,7 @@ def timeit(fn, reps=5):
 PAIR = int(os.environ.get('MB_PAIR', '-1'))
 STRIP = int(os.environ.get('MB_STRIP', '-1'))
 ONLY = os.environ.get('MB_ONLY', '')        # substring filter on the case name
+F8 = int(os.environ.get('MB_F8', '0'))      # 1: the 3x3 convs in the F8 cross-term mode (layers behind the VQ)
 
 
 def conv_case(name, B, H, W, Cin, Cout, ksize=3, up=0, res=False, act=0, split=False, bias=True, slice_kb=0):
@@ -37,14 +38,18 @@ def conv_case(name, B, H, W, Cin, Cout, ksize=3, up=0, res=False, act=0, split=F
     lo = (torch.randn(B, H, W, Cin, device=dev) * 1e-4).half()
     w = torch.randn(Cout, Cin, ksize, ksize, device=dev) * 0.03
     blob = G.tc_pack_up2(w) if up else G.tc_pack(w)
+    f8 = 1 if (F8 and ksize == 3 and not slice_kb) else 0
+    if f8:
+        hi, lo = G.tc_prepare_f8(torch.randn(B, H, W, Cin, device=dev) * 0.5)
+        blob = G.tc_pack_f8(w, up2=bool(up))
     b = torch.randn(Cout, device=dev) if bias else None
     u = 2 if up else 1
     y = None if split else torch.empty(B, H * u, W * u, Cout, device=dev)
     r = torch.randn(B, H * u, W * u, Cout, device=dev) if res else None
-    fn = lambda: G.tc_igemm(hi, lo, blob, b, Cout, ksize, act=act, res1=r, y=y, upsample=up, split_out=split, pair=PAIR, strip=STRIP, slice_kb=slice_kb)
+    fn = lambda: G.tc_igemm(hi, lo, blob, b, Cout, ksize, act=act, res1=r, y=y, upsample=up, split_out=split, pair=PAIR, strip=STRIP, slice_kb=slice_kb, f8=f8)
     ms = timeit(fn)
     flops = 2.0 * B * H * u * W * u * Cout * Cin * ksize * ksize
-    execd = 3 * 2.0 * B * H * W * Cout * Cin * (4 * 4 if up else ksize * ksize)
+    execd = (2 if f8 else 3) * 2.0 * B * H * W * Cout * Cin * (4 * 4 if up else ksize * ksize)
     print(f"{name:34s} {ms:8.3f} ms  algorithmic {flops / ms / 1e9:7.1f} TF/s  executed {execd / ms / 1e9:7.1f} TF/s")
     return ms
 

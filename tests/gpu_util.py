@@ -86,6 +86,30 @@ def tc_prepare(x_nhwc, mode=0, pro_a=None, pro_b=None, gamma=None, beta=None, up
     return hi, lo
 
 
+def tc_pack_f8(w_oihw, up2=False):
+    """F8 cross-term packing of a conv weight (second plane: interleaved e4m3 bytes); up2: the sub-pixel phase filters."""
+    lib = L.load()
+    co, ci, kh, kw = w_oihw.shape
+    w = w_oihw.contiguous()
+    if up2:
+        blob = torch.empty(lib.femasr_tc_weight_bytes(4 * co, ci, 2, 2), dtype=torch.uint8, device=w.device)
+        L.check(lib.femasr_tc_pack_weight_up2_f8(p(w), p(blob), co, ci, S()))
+    else:
+        blob = torch.empty(lib.femasr_tc_weight_bytes(co, ci, kh, kw), dtype=torch.uint8, device=w.device)
+        L.check(lib.femasr_tc_pack_weight_f8(p(w), p(blob), co, ci, kh, kw, S()))
+    return blob
+
+
+def tc_prepare_f8(x_nhwc, mode=0, pro_a=None, pro_b=None):
+    """fp16 hi plane + the interleaved e4m3 plane (same byte size as a lo plane) of the F8 cross-term mode."""
+    lib = L.load()
+    B, H, W, Cc = x_nhwc.shape
+    hi = torch.empty(B, H, W, Cc, dtype=torch.float16, device=x_nhwc.device)
+    x8 = torch.empty(B, H, W, Cc, dtype=torch.float16, device=x_nhwc.device)      # raw bytes
+    L.check(lib.femasr_tc_prepare_f8(p(x_nhwc), p(hi), p(x8), mode, p(pro_a), p(pro_b), B, H, W, Cc, S()))
+    return hi, x8
+
+
 def tc_pack_up2(w_oihw):
     lib = L.load()
     co, ci, _, _ = w_oihw.shape
@@ -96,7 +120,7 @@ def tc_pack_up2(w_oihw):
 
 
 def tc_igemm(hi, lo, blob, bias, Cout, ksize=3, act=0, res1=None, res2=None, y=None, upsample=0, split_out=False,
-             gn_partial=None, stride=1, kb_begin=0, kb_count=0, slice_kb=0, pair=-1, strip=-1):
+             gn_partial=None, stride=1, kb_begin=0, kb_count=0, slice_kb=0, pair=-1, strip=-1, f8=0):
     lib = L.load()
     B, H, W, Cin = hi.shape
     u = 2 if upsample else 1
@@ -108,7 +132,7 @@ def tc_igemm(hi, lo, blob, bias, Cout, ksize=3, act=0, res1=None, res2=None, y=N
     elif y is None:
         y = torch.empty(B, Ho, Wo, Cout, device=hi.device)
     a = L.TcArgs(p(hi), p(lo), p(blob), p(bias), p(res1), p(res2), p(y), B, H, W, Cin, Cout, ksize, act,
-                 p(oh), p(ol), stride, kb_begin, kb_count, slice_kb, pair, strip, p(gn_partial), upsample)
+                 p(oh), p(ol), stride, kb_begin, kb_count, slice_kb, pair, strip, p(gn_partial), upsample, f8)
     L.check(lib.femasr_tc_igemm(C.byref(a), S()))
     return (oh, ol) if split_out else y
 

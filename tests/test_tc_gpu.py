@@ -315,3 +315,32 @@ def test_stage_taps_tensor_core_path(cuda):
     for n, v in report.items():
         assert v <= 2e-4, f"stage {n}: relative max error {v:.3e}"
     assert (out.cpu() - want).abs().max().item() <= 1e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,kw", [
+    (1, 24, 40, 256, 256, {}),                 # generic tiles, CTA pair
+    (1, 9, 384, 128, 128, {}),                 # row strips, streamed weights
+    (2, 10, 256, 64, 64, {}),                  # multi-row strips, resident weights
+    (1, 12, 20, 256, 128, {"upsample": 1}),    # sub-pixel phase filters
+    (2, 33, 17, 128, 64, {"pair": 0})])
+def test_tc_f8_cross_terms(cuda, B, H, W, Cin, Cout, kw):
+    """F8 mode (layers behind the VQ): a_hi*w_hi on fp16 plus ONE e4m3 product for both cross terms.  The cross terms are
+    2^-11 of the main one and carry a relative error of ~2^-4 each, so the result sits ~2^-14 from the 3-product one:
+    well inside the 1e-3 output budget of those layers (scripts/exp_fp8_cross.py: 1.2e-4 end to end), far better than
+    the main product alone."""
+    up = kw.get("upsample", 0)
+    x, w, b = rnd(B, Cin, H, W, seed=60), rnd(Cout, Cin, 3, 3, seed=61, scale=0.03), rnd(Cout, seed=62)
+    xin = O.upsample2(x) if up else x
+    want = F.conv2d(xin.double(), w.double(), b.double(), padding=1)
+    xg, bg = G.nhwc(x).to(cuda), b.to(cuda)
+    hi, lo = G.tc_prepare(xg)
+    y3 = G.tc_igemm(hi, lo, G.tc_pack_up2(w.to(cuda)) if up else G.tc_pack(w.to(cuda)), bg, Cout, 3, **kw)
+    h8, x8 = G.tc_prepare_f8(xg)
+    assert torch.equal(h8, hi)
+    y2 = G.tc_igemm(h8, x8, G.tc_pack_f8(w.to(cuda), up2=bool(up)), bg, Cout, 3, f8=1, **kw)
+    zero = torch.zeros_like(lo)
+    y1 = G.tc_igemm(hi, zero, G.tc_pack_up2(w.to(cuda)) if up else G.tc_pack(w.to(cuda)), bg, Cout, 3, **kw)   # (no a_lo term)
+    e3, e2, e1 = rel_err(G.nchw(y3), want), rel_err(G.nchw(y2), want), rel_err(G.nchw(y1), want)
+    print(f"f8 cross {B}x{H}x{W} {Cin}->{Cout} {kw}: rel err 3-product {e3:.2e}, fp16 + fp8 cross {e2:.2e}, without a_lo {e1:.2e}")
+    assert e3 <= 2e-5
+    assert e2 <= 1.5e-4 and e2 < 0.35 * e1
