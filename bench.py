@@ -414,7 +414,10 @@ def main():
                 "launches_per_step": d["launches"] // 2, "avg_launch_ms": round(d["ms"] / max(1, d["launches"]), 4),
                 "share_of_step": round(d["ms"] / tot_ms, 4) if tot_ms else None,
                 "flops_counted": "algorithmic 2*MAC of the convs/linears this kernel executed",
-                "arithmetic": "fp32 FFMA (SIMT)" if gemm_path == 0 else "tcgen05 kind::f16, 3-MMA split-fp16 (hi*hi+hi*lo+lo*hi), fp32 accumulate in TMEM",
+                "arithmetic": "fp32 FFMA (SIMT)" if gemm_path == 0 else (
+                    "tcgen05, fp32 accumulate in TMEM; in front of the VQ 3-MMA split-fp16 kind::f16 (hi*hi+hi*lo+lo*hi); behind it "
+                    + ("a_hi*w_hi on kind::f16 + ONE kind::f8f6f4 e4m3 product for both cross terms (2.0 MMA units per algorithmic MMA)"
+                       if os.environ.get("FEMASR_F8_CROSS", "1") != "0" else "the same 3 products")),
                 "path_tflops": round(flops_step / (ms_step / 1e3) / 1e12, 2),
                 "path_frac": round(flops_step / (ms_step / 1e3) / 1e12 / peak, 4),
                 "kernels": {k: {"launches": v["launches"] // 2, "ms_per_step": round(v["ms"] / 2, 3)} for k, v in prof.items()}}

@@ -1156,50 +1156,57 @@ __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float
   return lo | (hi << 16);
 }
 template <int MODE>
-__global__ void __launch_bounds__(256) tc_prepare_flat_f8_kernel(const float4* __restrict__ x, uint2* __restrict__ hi,
-                                                                 uint32_t* __restrict__ x8, const float* __restrict__ sc,
-                                                                 const float* __restrict__ sh, int C, int per_image4) {
+__global__ void __launch_bounds__(256) tc_prepare_flat_f8_kernel(const float4* __restrict__ x, uint4* __restrict__ hi,
+                                                                 uint2* __restrict__ x8, const float* __restrict__ sc,
+                                                                 const float* __restrict__ sh, int C, int per_image8) {
+  // one thread = 8 consecutive channels of a pixel: 32 bytes in, 16 (hi) + 8 (lo8) + 8 (value8) bytes out
+  constexpr int U = 2;
   const int b = blockIdx.y;
-  const long base = (long)b * per_image4;
-  const int i0 = blockIdx.x * (256 * PREP_U) + threadIdx.x;
-  const int c4 = C >> 2;
-  float4 v[PREP_U];
+  const long base = (long)b * per_image8;
+  const int i0 = blockIdx.x * (256 * U) + threadIdx.x;
+  const int c8 = C >> 3;
+  float4 v[U][2];
 #pragma unroll
-  for (int u = 0; u < PREP_U; ++u) {
+  for (int u = 0; u < U; ++u) {
     const int i = i0 + u * 256;
-    if (i < per_image4) v[u] = __ldg(x + base + i);
+    if (i < per_image8) { v[u][0] = __ldg(x + 2 * (base + i)); v[u][1] = __ldg(x + 2 * (base + i) + 1); }
   }
 #pragma unroll
-  for (int u = 0; u < PREP_U; ++u) {
+  for (int u = 0; u < U; ++u) {
     const int i = i0 + u * 256;
-    if (i >= per_image4) break;
-    float w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-    const int cq = i % c4;                     // float4 index inside the pixel
-    const int c = cq * 4;
+    if (i >= per_image8) break;
+    float w[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+    const int c = (i % c8) * 8;
     if (MODE == FEMASR_PRO_GN_SILU || MODE == FEMASR_PRO_GN_SILU_FAST) {
-      const float4 s = __ldg(reinterpret_cast<const float4*>(sc + (long)b * C + c));
-      const float4 t = __ldg(reinterpret_cast<const float4*>(sh + (long)b * C + c));
-      const float ss[4] = {s.x, s.y, s.z, s.w}, tt[4] = {t.x, t.y, t.z, t.w};
+      const float4* ps = reinterpret_cast<const float4*>(sc + (long)b * C + c);
+      const float4* pt = reinterpret_cast<const float4*>(sh + (long)b * C + c);
+      const float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), t0 = __ldg(pt), t1 = __ldg(pt + 1);
+      const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const float tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 8; ++k) {
         const float n = fmaf(w[k], ss[k], tt[k]);
         w[k] = MODE == FEMASR_PRO_GN_SILU_FAST ? __fdividef(n, 1.0f + __expf(-n)) : silu_f(n);
       }
     }
-    __align__(8) __half h[4];
-    float l[4], cl[4];
+    float l[8];
+    uint32_t hp[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      cl[k] = fminf(fmaxf(w[k], -65504.f), 65504.f);
-      h[k] = __float2half_rn(cl[k]);
-      l[k] = (cl[k] - __half2float(h[k])) * F8_LO_SCALE;
+      uint32_t lo_unused;
+      const float a = fminf(fmaxf(w[2 * k], -65504.f), 65504.f), bq = fminf(fmaxf(w[2 * k + 1], -65504.f), 65504.f);
+      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hp[k]) : "f"(bq), "f"(a));
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hp[k]));
+      l[2 * k] = (a - hf.x) * F8_LO_SCALE; l[2 * k + 1] = (bq - hf.y) * F8_LO_SCALE;
+      w[2 * k] = a; w[2 * k + 1] = bq;
+      (void)lo_unused;
     }
-    hi[base + i] = *reinterpret_cast<const uint2*>(h);
-    // byte layout of the pixel's x8 row: chunk (c / 64) * 128 + (c % 64) for the lo part, + 64 for the hi part
-    const long pix = (base + i) / c4;
-    const long word = pix * (C >> 1) + (c >> 6) * 32 + ((c & 63) >> 2);
-    x8[word] = pack_e4m3x4(l[0], l[1], l[2], l[3]);
-    x8[word + 16] = pack_e4m3x4(cl[0], cl[1], cl[2], cl[3]);
+    hi[base + i] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    // byte layout of the pixel's x8 row: chunk (c / 64) * 128 + (c % 64) for the lo part, + 64 for the value part
+    const long pix = (base + i) / c8;
+    const long q = pix * (C >> 2) + (c >> 6) * 16 + ((c & 63) >> 3);          // index in 8-byte units
+    x8[q] = make_uint2(pack_e4m3x4(l[0], l[1], l[2], l[3]), pack_e4m3x4(l[4], l[5], l[6], l[7]));
+    x8[q + 8] = make_uint2(pack_e4m3x4(w[0], w[1], w[2], w[3]), pack_e4m3x4(w[4], w[5], w[6], w[7]));
   }
 }
 
@@ -1562,17 +1569,17 @@ extern "C" int femasr_tc_prepare_f8(const float* x, void* a_hi, void* a_x8, int 
   FEMASR_CHECK_ARG(C % 64 == 0, "tc_prepare_f8: C must be a multiple of 64");
   FEMASR_CHECK_ARG((long)H * W * (C / 4) < (1l << 30) && B <= 65535, "tc_prepare_f8: tensor too large for the flat kernel");
   cudaStream_t st = as_stream(stream);
-  const int per4 = H * W * (C / 4);
-  const dim3 grid((unsigned)cdiv(per4, 256 * PREP_U), (unsigned)B);
+  const int per8 = H * W * (C / 8);
+  const dim3 grid((unsigned)cdiv(per8, 256 * 2), (unsigned)B);
   const float4* x4 = reinterpret_cast<const float4*>(x);
-  uint2* hi = reinterpret_cast<uint2*>(a_hi);
-  uint32_t* x8 = reinterpret_cast<uint32_t*>(a_x8);
+  uint4* hi = reinterpret_cast<uint4*>(a_hi);
+  uint2* x8 = reinterpret_cast<uint2*>(a_x8);
   if (mode == FEMASR_PRO_GN_SILU || mode == FEMASR_PRO_GN_SILU_FAST) {
     FEMASR_CHECK_ARG(pro_a && pro_b, "tc_prepare_f8: GN mode needs the scale/shift tables");
-    if (mode == FEMASR_PRO_GN_SILU) tc_prepare_flat_f8_kernel<FEMASR_PRO_GN_SILU><<<grid, 256, 0, st>>>(x4, hi, x8, pro_a, pro_b, C, per4);
-    else tc_prepare_flat_f8_kernel<FEMASR_PRO_GN_SILU_FAST><<<grid, 256, 0, st>>>(x4, hi, x8, pro_a, pro_b, C, per4);
+    if (mode == FEMASR_PRO_GN_SILU) tc_prepare_flat_f8_kernel<FEMASR_PRO_GN_SILU><<<grid, 256, 0, st>>>(x4, hi, x8, pro_a, pro_b, C, per8);
+    else tc_prepare_flat_f8_kernel<FEMASR_PRO_GN_SILU_FAST><<<grid, 256, 0, st>>>(x4, hi, x8, pro_a, pro_b, C, per8);
   } else if (mode == FEMASR_PRO_NONE) {
-    tc_prepare_flat_f8_kernel<FEMASR_PRO_NONE><<<grid, 256, 0, st>>>(x4, hi, x8, nullptr, nullptr, C, per4);
+    tc_prepare_flat_f8_kernel<FEMASR_PRO_NONE><<<grid, 256, 0, st>>>(x4, hi, x8, nullptr, nullptr, C, per8);
   } else {
     return fail(FEMASR_ERR_ARG, "tc_prepare_f8: bad mode");
   }

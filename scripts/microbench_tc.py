@@ -86,6 +86,8 @@ def prep_case(name, B, H, W, C, mode):
     hi = torch.empty(B, H, W, C, dtype=torch.float16, device=dev); lo = torch.empty_like(hi)
     lib = L.load()
     fn = lambda: L.check(lib.femasr_tc_prepare(G.p(x), G.p(hi), G.p(lo), mode, G.p(sc), G.p(sh), None, None, B, H, W, C, 0, 1e-6, G.S()))
+    if name.startswith("prep f8"):
+        fn = lambda: L.check(lib.femasr_tc_prepare_f8(G.p(x), G.p(hi), G.p(lo), mode, G.p(sc), G.p(sh), B, H, W, C, G.S()))
     ms = timeit(fn)
     print(f"{name:34s} {ms:8.3f} ms  {x.numel() * 8 / ms / 1e6:7.1f} GB/s (4 B read + 4 B written per element)")
 
@@ -96,3 +98,6 @@ for mode, tag in ((1, "exact"), (3, "fast")):
     prep_case(f"prep {tag} 128ch @256x256", 32, 256, 256, 128, mode)
     prep_case(f"prep {tag} 256ch @128x128", 32, 128, 128, 256, mode)
 prep_case("prep none 256ch @64x64", 32, 64, 64, 256, 0)
+prep_case("prep f8 fast 64ch @512x512", 32, 512, 512, 64, 3)
+prep_case("prep f8 fast 128ch @256x256", 32, 256, 256, 128, 3)
+prep_case("prep f8 fast 256ch @128x128", 32, 128, 128, 256, 3)
