@@ -271,7 +271,7 @@ constexpr int STRIP_PLANE_BYTES = 17 * 1024;          // 130 rows x 128 B = 16,6
 // These layers are L2->SM bound and 60 % of their remaining L2 traffic was the weight tile re-fetched per tile.
 template <int BN, bool PAIR, bool STRIP, bool BRES = false>
 struct TcCfg {
-  static_assert(!(PAIR && STRIP), "strip tiles are single-CTA");
+  static_assert(!(PAIR && BRES), "resident-weight strips are single-CTA");
   static_assert(!BRES || (STRIP && BN == 64), "resident weights: strip mode, 64-wide tiles");
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;                 // weight-tile rows this CTA stages
   static constexpr int B_PLANE_BYTES = B_ROWS * TC_BK * 2;
@@ -499,26 +499,42 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           if (PF_STRIPS > 0) prefetch_next();
           mbar_wait(emptyA_bar(sa), pa ^ 1u);
           const uint32_t a_dst = smem_base + Cfg::B_RES_BYTES + sa * Cfg::SA_BYTES;
-          mbar_expect_tx(fullA_bar(sa), 2 * STRIP_PX * TC_BK * 2);
-          tma_load_4d(a_dst, &map_a_hi, fullA_bar(sa), c0, x0 - 1, y0 + sr - 1, tc.b);
-          tma_load_4d(a_dst + Cfg::SA_PLANE, &map_a_lo, fullA_bar(sa), c0, x0 - 1, y0 + sr - 1, tc.b);
+          if (PAIR) {
+            // CTA pair over two neighbouring row tiles: each CTA stages its own strip and HALF of every weight tile;
+            // all loads complete on the LEADER's barriers, armed once for the bytes of both CTAs
+            const uint32_t lead = map_to_cta(fullA_bar(sa), 0);
+            if (rank == 0) mbar_expect_tx(fullA_bar(sa), 2 * (2 * STRIP_PX * TC_BK * 2));
+            tma2_load_4d(a_dst, &map_a_hi, lead, c0, x0 - 1, y0 + sr - 1, tc.b);
+            tma2_load_4d(a_dst + Cfg::SA_PLANE, &map_a_lo, lead, c0, x0 - 1, y0 + sr - 1, tc.b);
+          } else {
+            mbar_expect_tx(fullA_bar(sa), 2 * STRIP_PX * TC_BK * 2);
+            tma_load_4d(a_dst, &map_a_hi, fullA_bar(sa), c0, x0 - 1, y0 + sr - 1, tc.b);
+            tma_load_4d(a_dst + Cfg::SA_PLANE, &map_a_lo, fullA_bar(sa), c0, x0 - 1, y0 + sr - 1, tc.b);
+          }
           if (++sa == Cfg::SA_STAGES) { sa = 0; pa ^= 1u; }
           if (BRES) continue;
           for (int kw = 0; kw < 3; ++kw) {                 // streamed weights (MR == 1: sr is kh)
             const int tap = sr * 3 + kw;
             mbar_wait(emptyB_bar(sb), pb ^ 1u);
             const uint32_t b_dst = smem_base + Cfg::SA_STAGES * Cfg::SA_BYTES + sb * Cfg::SB_BYTES;
-            (void)n0;
-            mbar_expect_tx(fullB_bar(sb), Cfg::SB_BYTES);
-            tma_load_2d(b_dst, &map_b_hi, fullB_bar(sb), tap * p.Cin + c0, n0);
-            tma_load_2d(b_dst + Cfg::B_PLANE_BYTES, &map_b_lo, fullB_bar(sb), tap * p.Cin + c0, n0);
+            if (PAIR) {
+              const uint32_t lead = map_to_cta(fullB_bar(sb), 0);
+              const int nh = n0 + (int)rank * (BN / 2);
+              if (rank == 0) mbar_expect_tx(fullB_bar(sb), 2 * Cfg::SB_BYTES);
+              tma2_load_2d(b_dst, &map_b_hi, lead, tap * p.Cin + c0, nh);
+              tma2_load_2d(b_dst + Cfg::B_PLANE_BYTES, &map_b_lo, lead, tap * p.Cin + c0, nh);
+            } else {
+              mbar_expect_tx(fullB_bar(sb), Cfg::SB_BYTES);
+              tma_load_2d(b_dst, &map_b_hi, fullB_bar(sb), tap * p.Cin + c0, n0);
+              tma_load_2d(b_dst + Cfg::B_PLANE_BYTES, &map_b_lo, fullB_bar(sb), tap * p.Cin + c0, n0);
+            }
             if (++sb == Cfg::SB_STAGES) { sb = 0; pb ^= 1u; }
           }
         }
     }
-  } else if (STRIP && warp == 1 && elect_one()) {
-    // ===================== MMA issuer (strip mode) =====================
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  } else if (STRIP && warp == 1 && rank == 0 && elect_one()) {
+    // ===================== MMA issuer (strip mode; leader CTA only when paired) =====================
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
     int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
     int set = 0; uint32_t set_phase = 0;           // accumulator set (MR slots) of the current work item
     if (BRES) { mbar_wait(bar_base + 8u * (2 * Cfg::SA_STAGES), 0u); tc_fence_after(); }   // weights resident
@@ -558,22 +574,34 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
               for (int k = 0; k < TC_BK / 16; ++k) {
                 const uint64_t ko = (uint64_t)((k * 32) >> 4);
                 const uint32_t first = (kh | cc | kw | k) ? 1u : 0u;
-                if (p.f8) {
-                  umma_f8(d_tmem, a_lo + ko, b_lo + ko, idesc, first);         // sum a_lo8 w_hi8 + sum a_hi8 w_lo8
+                if (PAIR) {
+                  if (p.f8) {
+                    umma2_f8(d_tmem, a_lo + ko, b_lo + ko, idesc, first);
+                  } else {
+                    umma2_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+                    umma2_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                  }
+                  umma2_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
                 } else {
-                  umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
-                  umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                  if (p.f8) {
+                    umma_f8(d_tmem, a_lo + ko, b_lo + ko, idesc, first);       // sum a_lo8 w_hi8 + sum a_hi8 w_lo8
+                  } else {
+                    umma_f16(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+                    umma_f16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                  }
+                  umma_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
                 }
-                umma_f16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
               }
               if (!BRES) {
-                umma_commit(emptyB_bar(sb));
+                if (PAIR) umma2_commit_mc(emptyB_bar(sb)); else umma_commit(emptyB_bar(sb));
                 if (++sb == Cfg::SB_STAGES) { sb = 0; pb ^= 1u; }
               }
             }
-            if (kh == 2 && cc == p.cchunks - 1) umma_commit(tfull_bar(slot));    // output row r complete
+            if (kh == 2 && cc == p.cchunks - 1) {                                // output row r complete
+              if (PAIR) umma2_commit_mc(tfull_bar(slot)); else umma_commit(tfull_bar(slot));
+            }
           }
-          umma_commit(emptyA_bar(sa));
+          if (PAIR) umma2_commit_mc(emptyA_bar(sa)); else umma_commit(emptyA_bar(sa));
           if (++sa == Cfg::SA_STAGES) { sa = 0; pa ^= 1u; }
         }
       if (++set == 2) { set = 0; set_phase ^= 1u; }
@@ -1427,7 +1455,7 @@ static int launch_tc_v(const CUtensorMap& ah, const CUtensorMap& al, const CUten
     const int phases = p.up ? 4 : 1;
     const int work = phases * ((num_m / phases + 1) / 2) * p.n_tiles;
     const int pairs = work < sm_count() / 2 ? work : sm_count() / 2;
-    FEMASR_CUDA(launch_pdl(tc_igemm_kernel<BN, true, false, false, RES>, dim3(2 * pairs), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, 2,
+    FEMASR_CUDA(launch_pdl(tc_igemm_kernel<BN, true, STRIP, false, RES>, dim3(2 * pairs), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, 2,
                            ah, al, bh, bl, om.y, om.oh, om.ol, p));
     return launch_status("tc_igemm_kernel(pair)");
   }
@@ -1504,7 +1532,13 @@ static TilePlan plan_tiles(const femasr_tc_args* a, int H, int W) {
                         a->kb_count == 0 && a->slice_kb == 0;
   t.strip = strip_ok && (strip_req >= 0 ? strip_req != 0 : true);
   if (t.strip) {
-    t.pair = false;
+    // strips over a CTA pair (two neighbouring row tiles share every weight tile, each CTA stages half of it): 128-wide
+    // tiles with streamed weights only.  Default on (FEMASR_TC_STRIP_PAIR=0 / a->pair = 0: single-CTA strips): the
+    // 128 -> 128 @256² convs re-stream the whole 590 KB weight matrix per row tile and are L2-bound in F8 mode;
+    // same-box: 1.156 -> 1.056 ms (F8), 1.490 -> 1.412 ms (three fp16 products), bit-identical results
+    static const int sp_env = [] { const char* e = getenv("FEMASR_TC_STRIP_PAIR"); return e ? atoi(e) : -1; }();
+    const bool bres_like = a->Cin == 64 && a->Cout == 64;
+    t.pair = t.BN == 128 && !bres_like && (pair_req >= 0 ? pair_req != 0 : (sp_env >= 0 ? sp_env != 0 : true));
     t.Wt = 128; t.Ht = 1;
   } else {
     tc_tile_shape(H, W, &t.Wt, &t.Ht);   // the widest power-of-two Wt <= 128 that wastes the fewest padded pixels
@@ -1795,6 +1829,7 @@ extern "C" int femasr_tc_igemm(const femasr_tc_args* a, void* stream) {
   }
   cudaStream_t st = as_stream(stream);
   if (strip) {
+    if (BN == 128 && pair) return launch_tc<128, true, true>(mah, mal, mbh, mbl, om, p, st);
     if (BN == 128) return launch_tc<128, false, true>(mah, mal, mbh, mbl, om, p, st);
     if (bres) return launch_tc<64, false, true, true>(mah, mal, mbh, mbl, om, p, st);
     return launch_tc<64, false, true>(mah, mal, mbh, mbl, om, p, st);

@@ -164,7 +164,7 @@ def test_tc_cta_pair(cuda, B, H, W, Cin, Cout, kw):
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 6, 128, 64, 64), (2, 5, 200, 64, 64), (1, 9, 384, 128, 128),
-                                           (1, 4, 130, 256, 128), (2, 7, 256, 128, 64),
+                                           (1, 4, 130, 256, 128), (2, 7, 256, 128, 64), (3, 40, 256, 128, 128),
                                            # 64 -> 64: weights resident in smem; > 148 tiles so CTAs loop over several
                                            (4, 48, 256, 64, 64)])
 def test_tc_strip_mode(cuda, B, H, W, Cin, Cout):
@@ -183,6 +183,14 @@ def test_tc_strip_mode(cuda, B, H, W, Cin, Cout):
     assert e <= 2e-5
     # same products, different accumulation order (kh, chunk, kw instead of tap, chunk): equal up to accumulator rounding
     assert (y0 - y1).abs().max().item() <= 1e-5 * y0.abs().max().item()
+    if Cout == 128:
+        # strips over a CTA pair (two neighbouring row tiles, each CTA stages half of every weight tile): same MMAs, same order
+        y2 = G.tc_igemm(hi, lo, blob, bg, Cout, 3, res1=res, strip=1, pair=1)
+        assert torch.equal(y1, y2), "the paired strip kernel must be bit-identical to the single-CTA one"
+        h8, x8 = G.tc_prepare_f8(G.nhwc(x).to(cuda))
+        b8 = G.tc_pack_f8(w.to(cuda))
+        assert torch.equal(G.tc_igemm(h8, x8, b8, bg, Cout, 3, res1=res, strip=1, pair=0, f8=1),
+                           G.tc_igemm(h8, x8, b8, bg, Cout, 3, res1=res, strip=1, pair=1, f8=1))
 
 
 def test_in_conv_split_planes(cuda):
