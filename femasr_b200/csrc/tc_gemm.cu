@@ -232,7 +232,7 @@ struct TcP {
                                  // fp32 running sum kept in the second TMEM buffer (round-to-nearest adds by the
                                  // epilogue warps), so the truncating MMA accumulator never runs longer than a slice
   int f8;                        // F8 mode: the "lo" planes of both operands hold interleaved e4m3 bytes per 64-channel chunk
-                                 // (A: [a_lo * 2^12 | a_hi], B: [w_hi * 2^-12 | w_lo]); one K = 128 fp8 product per k-block
+                                 // (A: [a_lo * 2^10 | a_hi * 2^-2], B: [w_hi * 2^-10 | w_lo * 2^2]); one K = 128 fp8 product per k-block
                                  // replaces the two fp16 cross products
   int tma_out;                   // 1: fp32 y, 2: split fp16 planes leave through TMA stores of the epilogue's staging tile
   int box_w, box_w_shift;        // a warp's 32 accumulator rows as a box of box_w x (32 / box_w) output pixels
@@ -1174,10 +1174,19 @@ __global__ void __launch_bounds__(256) tc_prepare_flat_kernel(const float4* __re
 }
 
 // F8 staging (layers behind the VQ): the hi plane as above; the second plane holds, per pixel and 64-channel chunk, 128
-// bytes = [e4m3((v - hi) * 2^12) x 64 | e4m3(v) x 64] - the A operand of the single K = 128 fp8 MMA group that replaces
-// the two fp16 cross products (the weights carry [e4m3(w_hi * 2^-12) | e4m3(w_lo)] at the matching offsets).
+// bytes = [e4m3((v - hi) * 2^10) x 64 | e4m3(v * 2^-2) x 64] - the A operand of the single K = 128 fp8 MMA group that
+// replaces the two fp16 cross products (the weights carry [e4m3(w_hi * 2^-10) | e4m3(w_lo * 2^2)] at the matching offsets,
+// so both power-of-two scales cancel inside the dot product).
 // Error budget: scripts/exp_fp8_cross.py, 1.2e-4 output max-abs for the whole post-VQ scope (bar 1e-3).
-constexpr float F8_LO_SCALE = 4096.0f;
+// The scales place the operands in e4m3's normal range (4 significant bits down to 2^-6, fewer below, nothing under 2^-10).
+// The first recipe, (2^12, 2^0), was tuned on the kaiming-uniform random-init weights, whose magnitudes all lie within a
+// factor 2 of the per-tensor maximum; a TRAINED conv is bell-shaped with typical |w| ~ max / 10 ... max / 50, for which
+// e4m3(w_hi * 2^-12) <= 0.25 * |w| / max is already subnormal.  scripts/exp_fp8_scales.py (weights of the layers behind the
+// VQ redrawn from a normal / a Student-t(3) distribution of the same standard deviation; output max-abs uniform / normal /
+// t(3)): (12, 0) 1.2e-4 / 1.1e-4 / 5.8e-4, (10, 2) 1.3e-4 / 1.4e-4 / 1.8e-4 - the minimax choice over a 10-recipe sweep.
+// Activations keep full e4m3 precision for |a| in [2^-4, 1792] (a_lo * 2^10 ~ a / 4 likewise).
+constexpr float F8_LO_SCALE = 1024.0f;       // a_lo * 2^10 against w_hi * 2^-10
+constexpr float F8_VAL_SCALE = 0.25f;        // a * 2^-2 against w_lo * 2^2
 __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
   const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
   const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
@@ -1234,7 +1243,8 @@ __global__ void __launch_bounds__(256) tc_prepare_flat_f8_kernel(const float4* _
     const long pix = (base + i) / c8;
     const long q = pix * (C >> 2) + (c >> 6) * 16 + ((c & 63) >> 3);          // index in 8-byte units
     x8[q] = make_uint2(pack_e4m3x4(l[0], l[1], l[2], l[3]), pack_e4m3x4(l[4], l[5], l[6], l[7]));
-    x8[q + 8] = make_uint2(pack_e4m3x4(w[0], w[1], w[2], w[3]), pack_e4m3x4(w[4], w[5], w[6], w[7]));
+    x8[q + 8] = make_uint2(pack_e4m3x4(w[0] * F8_VAL_SCALE, w[1] * F8_VAL_SCALE, w[2] * F8_VAL_SCALE, w[3] * F8_VAL_SCALE),
+                           pack_e4m3x4(w[4] * F8_VAL_SCALE, w[5] * F8_VAL_SCALE, w[6] * F8_VAL_SCALE, w[7] * F8_VAL_SCALE));
   }
 }
 
@@ -1321,7 +1331,7 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, __half* __res
 }
 
 // F8 variant of the packed weights: hi plane as above; the second plane holds per (row, 64-wide k chunk) 128 bytes =
-// [e4m3(w_hi * 2^-12) x 64 | e4m3(w_lo) x 64] (see tc_prepare_flat_f8_kernel)
+// [e4m3(w_hi * 2^-10) x 64 | e4m3(w_lo * 2^2) x 64] (see tc_prepare_flat_f8_kernel)
 __global__ void tc_pack_weight_f8_kernel(const float* __restrict__ w, __half* __restrict__ hi, uint8_t* __restrict__ x8,
                                          const unsigned int* __restrict__ absmax, float* __restrict__ inv_scale, int Cout,
                                          int Cin, int KH, int KW) {
@@ -1345,7 +1355,7 @@ __global__ void tc_pack_weight_f8_kernel(const float* __restrict__ w, __half* __
   const float hf = __half2float(h);
   uint8_t* row = x8 + (long)co * K * 2 + (k >> 6) * 128 + (k & 63);
   row[0] = (uint8_t)__nv_cvt_float_to_fp8(hf * (1.0f / F8_LO_SCALE), __NV_SATFINITE, __NV_E4M3);
-  row[64] = (uint8_t)__nv_cvt_float_to_fp8(v - hf, __NV_SATFINITE, __NV_E4M3);
+  row[64] = (uint8_t)__nv_cvt_float_to_fp8((v - hf) * (1.0f / F8_VAL_SCALE), __NV_SATFINITE, __NV_E4M3);
 }
 
 // nearest-x2 upsample followed by a 3x3 conv == four 2x2 convs on the low-res grid (one per output phase

@@ -217,7 +217,8 @@ int femasr_tc_prepare(const float* x, void* a_hi, void* a_lo, int mode, const fl
                       const float* gamma, const float* beta, int B, int H, int W, int C, int upsample,
                       float eps, void* stream);
 /* F8 cross-term mode (femasr_tc_args.f8): per 64-channel chunk the second operand plane holds 128 bytes
- * [e4m3(lo * 2^12) x 64 | e4m3(value) x 64] (activations) resp. [e4m3(w_hi * 2^-12) x 64 | e4m3(w_lo) x 64] (weights). */
+ * [e4m3(lo * 2^10) x 64 | e4m3(value * 2^-2) x 64] (activations) resp. [e4m3(w_hi * 2^-10) x 64 | e4m3(w_lo * 2^2) x 64]
+ * (weights); the scales cancel in the product and are an implementation detail of the prepare / pack pair. */
 int femasr_tc_prepare_f8(const float* x, void* a_hi, void* a_x8, int mode, const float* pro_a, const float* pro_b,
                          int B, int H, int W, int C, void* stream);
 int femasr_tc_pack_weight_f8(const float* w_oihw, void* blob, int Cout, int Cin, int kh, int kw, void* stream);

@@ -54,7 +54,8 @@ def main():
                 y = y + F.conv2d(e4m3(a_hi), e4m3(w_lo), None, stride=stride, padding=pad)
             elif mode["m"] in ("fixed_e4m3", "fixed_e5m2"):
                 # the recipe a kernel can use without any per-tensor statistics of the activations:
-                #   A8 = [e4m3(a_lo * 2^12) | e4m3(a_hi)],  B8 = [f8(w_hi * 2^(s-12)) | e4m3(w_lo * 2^s)],  s: max|w| * 2^s in [512, 1024)
+                #   A8 = [e4m3(a_lo * 2^10) | e4m3(a_hi * 2^-2)],  B8 = [f8(w_hi * 2^(s-10)) | e4m3(w_lo * 2^(s+2))],  s: max|w| * 2^s in [512, 1024)
+                # (scales: scripts/exp_fp8_scales.py)
                 mx = float(w.abs().max())
                 sc = 2.0 ** (10 - math.frexp(mx)[1])
                 ws = w * sc
@@ -63,8 +64,8 @@ def main():
                 f8hi = torch.float8_e4m3fn if mode["m"] == "fixed_e4m3" else torch.float8_e5m2
                 q = lambda t, dt=torch.float8_e4m3fn: t.clamp(-448, 448).to(dt).float()
                 y = F.conv2d(a_hi, wh, None, stride=stride, padding=pad)
-                y = y + F.conv2d(q(a_lo * 4096.0), q(wh / 4096.0, f8hi), None, stride=stride, padding=pad)
-                y = y + F.conv2d(q(a_hi), q(wl), None, stride=stride, padding=pad)
+                y = y + F.conv2d(q(a_lo * 1024.0), q(wh / 1024.0, f8hi), None, stride=stride, padding=pad)
+                y = y + F.conv2d(q(a_hi * 0.25), q(wl * 4.0), None, stride=stride, padding=pad)
                 y = y / sc + sd_[p + ".bias"].view(1, -1, 1, 1)
             elif mode["m"] == "exact3":
                 y = y + F.conv2d(a_lo, w_hi, None, stride=stride, padding=pad) + F.conv2d(a_hi, w_lo, None, stride=stride, padding=pad)
