@@ -29,6 +29,7 @@ PAIR = int(os.environ.get('MB_PAIR', '-1'))
 STRIP = int(os.environ.get('MB_STRIP', '-1'))
 ONLY = os.environ.get('MB_ONLY', '')        # substring filter on the case name
 F8 = int(os.environ.get('MB_F8', '0'))      # 1: the 3x3 convs in the F8 cross-term mode (layers behind the VQ)
+GN = int(os.environ.get('MB_GN', '0'))      # 1: the 3x3 convs also emit GroupNorm partial sums (what most of them do in the network)
 
 
 def conv_case(name, B, H, W, Cin, Cout, ksize=3, up=0, res=False, act=0, split=False, bias=True, slice_kb=0):
@@ -46,7 +47,10 @@ def conv_case(name, B, H, W, Cin, Cout, ksize=3, up=0, res=False, act=0, split=F
     u = 2 if up else 1
     y = None if split else torch.empty(B, H * u, W * u, Cout, device=dev)
     r = torch.randn(B, H * u, W * u, Cout, device=dev) if res else None
-    fn = lambda: G.tc_igemm(hi, lo, blob, b, Cout, ksize, act=act, res1=r, y=y, upsample=up, split_out=split, pair=PAIR, strip=STRIP, slice_kb=slice_kb, f8=f8)
+    gn = None
+    if GN and ksize == 3 and not split:
+        gn = torch.empty(B * G.tc_gn_rows(B, H, W, Cin, Cout, upsample=up, slice_kb=slice_kb, pair=PAIR, strip=STRIP) * 64, device=dev)
+    fn = lambda: G.tc_igemm(hi, lo, blob, b, Cout, ksize, act=act, res1=r, y=y, upsample=up, split_out=split, pair=PAIR, strip=STRIP, slice_kb=slice_kb, f8=f8, gn_partial=gn)
     ms = timeit(fn)
     flops = 2.0 * B * H * u * W * u * Cout * Cin * ksize * ksize
     execd = (2 if f8 else 3) * 2.0 * B * H * W * Cout * Cin * (4 * 4 if up else ksize * ksize)
