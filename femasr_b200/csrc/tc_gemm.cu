@@ -263,6 +263,10 @@ constexpr int A_PLANE_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 // (the swizzle follows absolute address bits, see the MMA issuer).  Activation traffic from L2 drops 2.9x (3 loads
 // instead of 9 per chunk) - the narrow layers are L2->SM bound (profiles/tc_igemm_traffic_r1.json).  Weights stream
 // through their own ring, one tap per stage.
+#ifndef FEMASR_BRES_MERGE
+#define FEMASR_BRES_MERGE 1       // 0: one N = 64 MMA per (output row, tap) in the resident-weight strip kernel (A/B knob)
+#endif
+constexpr bool BRES_MERGE = FEMASR_BRES_MERGE != 0;
 constexpr int STRIP_PX = 130;                         // 128 outputs + one halo pixel each side
 constexpr int STRIP_PLANE_BYTES = 17 * 1024;          // 130 rows x 128 B = 16,640 B, padded to the 1024-B swizzle period
 
@@ -470,12 +474,17 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     // per (kh, 64-channel chunk): one 130-pixel activation strip (hi, lo), then the three taps' weight tiles
     int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
     if (BRES) {
-      // the whole [64][9*64] weight matrix (hi, lo) once: tap t at smem_base + t * 2 * B_PLANE_BYTES
+      // the whole [64][9*64] weight matrix (hi, lo) once.  Merged layout (see the MMA issuer): per kw the hi planes of
+      // kh = 2, 1, 0 back to back (3 x 8 KB), then the three lo planes - any run of consecutive kh is ONE B operand of
+      // N = 64, 128 or 192 rows.  Plain layout: tap t at smem_base + t * 2 * B_PLANE_BYTES.
       const uint32_t bres_bar = bar_base + 8u * (2 * Cfg::SA_STAGES);
       mbar_expect_tx(bres_bar, Cfg::B_RES_BYTES);
       for (int tap = 0; tap < 9; ++tap) {
-        tma_load_2d(smem_base + tap * 2 * Cfg::B_PLANE_BYTES, &map_b_hi, bres_bar, tap * p.Cin, 0);
-        tma_load_2d(smem_base + tap * 2 * Cfg::B_PLANE_BYTES + Cfg::B_PLANE_BYTES, &map_b_lo, bres_bar, tap * p.Cin, 0);
+        const int kh = tap / 3, kw = tap - 3 * kh;
+        const uint32_t dst_hi = BRES_MERGE ? smem_base + (kw * 6 + (2 - kh)) * Cfg::B_PLANE_BYTES : smem_base + tap * 2 * Cfg::B_PLANE_BYTES;
+        const uint32_t dst_lo = dst_hi + (BRES_MERGE ? 3 : 1) * Cfg::B_PLANE_BYTES;
+        tma_load_2d(dst_hi, &map_b_hi, bres_bar, tap * p.Cin, 0);
+        tma_load_2d(dst_lo, &map_b_lo, bres_bar, tap * p.Cin, 0);
       }
     }
     // L2 prefetch cursor: runs PF_STRIPS strips ahead of the loads over the same (work, input row, chunk) sequence
@@ -539,6 +548,64 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     int set = 0; uint32_t set_phase = 0;           // accumulator set (MR slots) of the current work item
     if (BRES) { mbar_wait(bar_base + 8u * (2 * Cfg::SA_STAGES), 0u); tc_fence_after(); }   // weights resident
     for (int work = worker; work < num_work; work += nworkers) {
+      if constexpr (BRES && BRES_MERGE) {
+        // Multi-row strip tiles with MERGED tap rows.  ncu on these convs (profiles/ncu_r2_epilogue.json): the tensor-core
+        // pipe 81 % utilised with its math sub-pipe at 42 % - a 128 x 64 x 16 MMA streams 4 KB of A and 2 KB of B out of
+        // shared memory (~48 cycles at 128 B / clk) for 34 cycles of fp16 math (17 of e4m3 math): with N = 64 the operand
+        // fetch, not the math, occupies the pipe.  Input strip sr feeds tap row kh = sr - r of every output row r it
+        // touches WITH THE SAME A operand, and the accumulators of rows r, r + 1, ... sit side by side in TMEM, so those
+        // products are ONE MMA of N = 64 x rows against the weight rows of kh = sr - r_lo, ..., sr - r_hi (contiguous in
+        // the merged layout): 144 instead of 288 MMAs per 4-row work item, A fetched once per strip and k-step instead of
+        // once per (row, tap).  Every accumulator still receives its contributions in (kh, kw, k, product) order, so the
+        // results are bit-identical to the unmerged form.  Only the very first product into a fresh accumulator (kh = 0,
+        // kw = 0, k = 0) must overwrite instead of accumulate and is issued on its own.
+        auto idesc_n = [](int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24); };
+        for (int sr = 0; sr < MR + 2; ++sr) {         // p.cchunks == 1 (64 input channels)
+          mbar_wait(fullA_bar(sa), pa);
+          tc_fence_after();
+          const uint32_t a_base = smem_base + Cfg::B_RES_BYTES + sa * Cfg::SA_BYTES;
+          const int r_lo = sr - 2 > 0 ? sr - 2 : 0, r_hi = sr < MR - 1 ? sr : MR - 1;
+          const bool fresh = sr < MR;                  // output row r = sr (== r_hi) starts with this strip (its kh = 0 tap row)
+          if (fresh) { mbar_wait(tempty_bar(set * MR + sr), set_phase ^ 1u); tc_fence_after(); }
+          const int rows = r_hi - r_lo + 1;
+          const uint32_t d_all = tmem_base + (uint32_t)((set * MR + r_lo) * BN);
+          const uint32_t d_new = tmem_base + (uint32_t)((set * MR + r_hi) * BN);
+          const uint32_t id_all = idesc_n(BN * rows), id_old = idesc_n(BN * (rows - 1)), id_one = idesc_n(BN);
+          const int b_first = 2 - (sr - r_lo);         // weight plane (within the kw group) of the first merged row
+          for (int kw = 0; kw < 3; ++kw) {
+            const uint64_t a_hi = make_sw128_desc(a_base + kw * 128);
+            const uint64_t a_lo = make_sw128_desc(a_base + Cfg::SA_PLANE + kw * 128);
+            const uint32_t b_grp = smem_base + kw * 6 * Cfg::B_PLANE_BYTES;
+            const uint64_t b_hi = make_sw128_desc(b_grp + b_first * Cfg::B_PLANE_BYTES);
+            const uint64_t b_lo = make_sw128_desc(b_grp + (3 + b_first) * Cfg::B_PLANE_BYTES);
+            // the fresh row alone: the LAST of the merged rows (kh = 0 = plane 2 of the group)
+            const uint64_t b_hi_new = make_sw128_desc(b_grp + 2 * Cfg::B_PLANE_BYTES);
+            const uint64_t b_lo_new = make_sw128_desc(b_grp + 5 * Cfg::B_PLANE_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t ko = (uint64_t)((k * 32) >> 4);
+              if (fresh && kw == 0 && k == 0) {
+                // first product of the k-step: older rows accumulate, the fresh row overwrites
+                if (p.f8) {
+                  if (rows > 1) umma_f8(d_all, a_lo + ko, b_lo + ko, id_old, 1u);
+                  umma_f8(d_new, a_lo + ko, b_lo_new + ko, id_one, 0u);
+                } else {
+                  if (rows > 1) umma_f16(d_all, a_lo + ko, b_hi + ko, id_old, 1u);
+                  umma_f16(d_new, a_lo + ko, b_hi_new + ko, id_one, 0u);
+                }
+              } else {
+                if (p.f8) umma_f8(d_all, a_lo + ko, b_lo + ko, id_all, 1u);
+                else umma_f16(d_all, a_lo + ko, b_hi + ko, id_all, 1u);
+              }
+              if (!p.f8) umma_f16(d_all, a_hi + ko, b_lo + ko, id_all, 1u);
+              umma_f16(d_all, a_hi + ko, b_hi + ko, id_all, 1u);
+            }
+          }
+          if (sr >= 2) umma_commit(tfull_bar(set * MR + sr - 2));       // output row sr - 2 has all three tap rows
+          umma_commit(emptyA_bar(sa));
+          if (++sa == Cfg::SA_STAGES) { sa = 0; pa ^= 1u; }
+        }
+      } else
       for (int sr = 0; sr < MR + 2; ++sr)
         for (int cc = 0; cc < p.cchunks; ++cc) {
           mbar_wait(fullA_bar(sa), pa);
