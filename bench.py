@@ -290,20 +290,41 @@ def main():
         def __init__(self):
             shape = (B, 3, S * args.scale, S * args.scale)
             self.stage = [torch.empty(shape, device=dev) for _ in range(2)]
-            self.full = [torch.empty((world * B,) + shape[1:], device=dev) for _ in range(2)]
             self.done = [None, None]
-            self.stream = torch.cuda.Stream()
             self.i = 0
+            # Scheme: copy-engine peer writes (femasr_b200.parallel.PeerGather: no SM kernel next to the persistent
+            # tensor-core kernels) when the GPUs can map each other, else the NCCL all-gather; FEMASR_GATHER=nccl|p2p forces one.
+            want = os.environ.get("FEMASR_GATHER", "nccl")
+            self.peer = None
+            if want in ("auto", "p2p"):
+                try:
+                    from femasr_b200.parallel import PeerGather
+                    self.peer = PeerGather(shape, torch.float32, dev, rank, world, nbuf=2)
+                except Exception as ex:       # any rank failing raises on every rank (collective self-check): uniform fallback
+                    if want == "p2p":
+                        raise
+                    print(f"[bench] peer-copy gather unavailable ({type(ex).__name__}: {ex}); using NCCL", file=sys.stderr)
+                    self.peer = None
+            if self.peer is None:
+                self.full = [torch.empty((world * B,) + shape[1:], device=dev) for _ in range(2)]
+                self.stream = torch.cuda.Stream()
+            else:
+                self.full = self.peer.full
+                self.stream = self.peer.stream
+            self.scheme = "copy-engine peer writes over NVLink (CUDA IPC; no SM kernel)" if self.peer else "NCCL all-gather"
 
         def __call__(self, out):
             k = self.i & 1
             self.i += 1
             cur = torch.cuda.current_stream()
             if self.done[k] is not None:
-                cur.wait_event(self.done[k])          # staging buffer k is free once its previous all-gather finished
+                cur.wait_event(self.done[k])          # staging buffer k is free once its previous gather finished
             self.stage[k].copy_(out, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(cur)
+            if self.peer is not None:
+                self.done[k] = self.peer.push(k, self.stage[k], after=ready)
+                return
             with torch.cuda.stream(self.stream):
                 self.stream.wait_event(ready)
                 dist.all_gather_into_tensor(self.full[k], self.stage[k])
@@ -315,6 +336,9 @@ def main():
             torch.cuda.current_stream().wait_stream(self.stream)
 
     gather = Gather() if world > 1 else None
+    if gather:
+        config["parallelism"] = (f"dp{world} (batch shards; one all-gather of the output shards per step - {gather.scheme} - on a side "
+                                 "stream, overlapping the next step's forward; drained inside the timed region)")
 
     def step_resident():
         out = run_resident()
@@ -382,6 +406,10 @@ def main():
     prof = eng.profile()
     eng.set_profile(False)
 
+    if gather is not None and gather.peer is not None:
+        torch.cuda.synchronize()
+        gather.peer.close()               # unmap the peers' buffers while every exporting process is still alive
+        dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -47,6 +47,95 @@ def all_gather_outputs(local: torch.Tensor, counts: List[int], group: Optional[d
     return torch.cat([buf[r * mx: r * mx + c] for r, c in enumerate(counts)], 0)
 
 
+class PeerGather:
+    """All-gather of EQUAL output shards by copy-engine peer writes instead of an NCCL kernel (one node, one process per GPU).
+
+    Why: the tensor-core kernels of this path are persistent - 148 CTAs, one per SM, each with a STATIC share of the tiles
+    and the whole 227 KB of shared memory.  An NCCL all-gather kernel that overlaps them (side stream) takes a few SMs for
+    its own CTAs; the tc_igemm CTAs that find no SM start only when another CTA of the same launch has finished its share,
+    so every launch in that window runs for up to two shares.  Peer-to-peer `cudaMemcpyAsync` over NVLink runs on the DMA
+    engines and takes no SM.  Every rank owns `nbuf` gather buffers [world * B, ...]; their CUDA IPC handles are exchanged
+    once (the mechanism torch.multiprocessing uses), and `push(k, shard)` writes the rank's shard into slot `rank` of buffer
+    k on EVERY rank.  A buffer is complete on all ranks once every rank's pushes have finished (stream sync + barrier, or -
+    as in bench.py - a timed region that ends with the max over ranks of each rank's own completion).
+
+    Raises at construction when a peer cannot be mapped / accessed or the self-check against `all_gather_into_tensor`
+    fails; callers fall back to the NCCL collective.
+    """
+
+    def __init__(self, shard_shape, dtype, device: torch.device, rank: int, world: int, nbuf: int = 2,
+                 group: Optional[dist.ProcessGroup] = None):
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.rank, self.world, self.B = rank, world, int(shard_shape[0])
+        self.device = device
+        self.full, self.peer = [], []
+        # every step that can fail locally is followed by a collective vote, so that ALL ranks raise (and fall back) together
+        mine, why = None, ""
+        try:
+            for r in range(world):
+                if r != rank and not torch.cuda.can_device_access_peer(device.index, r):
+                    raise RuntimeError(f"no peer access {device.index} -> {r}")
+            tail = tuple(shard_shape[1:])
+            self.full = [torch.empty((world * self.B,) + tail, dtype=dtype, device=device) for _ in range(nbuf)]
+            mine = [reduce_tensor(t) for t in self.full]                # (rebuild function, picklable arguments)
+        except Exception as ex:                                         # noqa: BLE001 - reported through the vote
+            why = f"{type(ex).__name__}: {ex}"
+        everyone: list = [None] * world
+        dist.all_gather_object(everyone, mine, group=group)
+        if mine is not None and all(e is not None for e in everyone):
+            try:                                                        # peer[r][k]: rank r's buffer k, mapped into this process
+                self.peer = [self.full if r == rank else [fn(*args) for fn, args in everyone[r]] for r in range(world)]
+            except Exception as ex:                                     # noqa: BLE001
+                why = f"{type(ex).__name__}: {ex}"
+                self.peer = []
+        elif not why:
+            why = "another rank could not export its buffers"
+        self._vote(bool(self.peer), group, why or "another rank could not map its peers")
+        self.stream = torch.cuda.Stream(device=device)
+        self._self_check(group)
+
+    def _vote(self, ok: bool, group, why: str):
+        flag = torch.tensor([1 if ok else 0], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) != 1:
+            self.close()
+            raise RuntimeError(f"peer-copy all-gather unavailable ({why})")
+
+    def close(self):
+        """Drop the mapped peer buffers (before the process group goes away: the exporting process must outlive the maps)."""
+        self.peer = []
+
+    def push(self, k: int, shard: torch.Tensor, after: Optional[torch.cuda.Event] = None) -> torch.cuda.Event:
+        """Enqueue (on the gather's own stream, after `after`) the copies of `shard` into slot `rank` of buffer k on every
+        rank; returns the event that marks their completion on this rank."""
+        lo, hi = self.rank * self.B, (self.rank + 1) * self.B
+        with torch.cuda.stream(self.stream):
+            if after is not None:
+                self.stream.wait_event(after)
+            for d in range(self.world):                                 # start with the next rank: no common first target
+                r = (self.rank + 1 + d) % self.world
+                self.peer[r][k][lo:hi].copy_(shard, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return ev
+
+    def _self_check(self, group):
+        g = torch.Generator(device="cpu").manual_seed(1234 + self.rank)
+        probe = torch.rand((self.B,) + tuple(self.full[0].shape[1:]), generator=g).to(self.full[0].dtype).to(self.device)
+        want = torch.empty_like(self.full[0])
+        dist.all_gather_into_tensor(want, probe, group=group)
+        for k in range(len(self.full)):
+            self.full[k].zero_()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)
+        for k in range(len(self.full)):
+            self.push(k, probe)
+        self.stream.synchronize()
+        dist.barrier(group=group)                                       # every rank's pushes have landed
+        ok = all(torch.equal(self.full[k], want) for k in range(len(self.full)))
+        self._vote(ok, group, "self-check against all_gather_into_tensor failed")
+
+
 def sharded_forward(run: Callable[[torch.Tensor], torch.Tensor], x_global: torch.Tensor, rank: int, world: int,
                     group: Optional[dist.ProcessGroup] = None, out_shape_fn: Optional[Callable] = None) -> torch.Tensor:
     """Run `run` (e.g. FeMaSRNet.test) on this rank's contiguous slice of x_global [N,3,H,W] and return
