@@ -294,7 +294,7 @@ def main():
             self.i = 0
             # Scheme: copy-engine peer writes (femasr_b200.parallel.PeerGather: no SM kernel next to the persistent
             # tensor-core kernels) when the GPUs can map each other, else the NCCL all-gather; FEMASR_GATHER=nccl|p2p forces one.
-            want = os.environ.get("FEMASR_GATHER", "nccl")
+            want = os.environ.get("FEMASR_GATHER", "auto")
             self.peer = None
             if want in ("auto", "p2p"):
                 try:
