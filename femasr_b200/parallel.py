@@ -124,16 +124,24 @@ class PeerGather:
         probe = torch.rand((self.B,) + tuple(self.full[0].shape[1:]), generator=g).to(self.full[0].dtype).to(self.device)
         want = torch.empty_like(self.full[0])
         dist.all_gather_into_tensor(want, probe, group=group)
-        for k in range(len(self.full)):
-            self.full[k].zero_()
-        torch.cuda.synchronize(self.device)
+        ok, why = True, "self-check against all_gather_into_tensor failed"
+        try:
+            for k in range(len(self.full)):
+                self.full[k].zero_()
+            torch.cuda.synchronize(self.device)
+        except Exception as ex:                                         # noqa: BLE001 - a local failure must not desynchronise the ranks
+            ok, why = False, f"{type(ex).__name__}: {ex}"
         dist.barrier(group=group)
-        for k in range(len(self.full)):
-            self.push(k, probe)
-        self.stream.synchronize()
+        try:
+            if ok:
+                for k in range(len(self.full)):
+                    self.push(k, probe)
+                self.stream.synchronize()
+        except Exception as ex:                                         # noqa: BLE001
+            ok, why = False, f"{type(ex).__name__}: {ex}"
         dist.barrier(group=group)                                       # every rank's pushes have landed
-        ok = all(torch.equal(self.full[k], want) for k in range(len(self.full)))
-        self._vote(ok, group, "self-check against all_gather_into_tensor failed")
+        ok = ok and all(torch.equal(self.full[k], want) for k in range(len(self.full)))
+        self._vote(ok, group, why)
 
 
 def sharded_forward(run: Callable[[torch.Tensor], torch.Tensor], x_global: torch.Tensor, rank: int, world: int,
