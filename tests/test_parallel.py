@@ -98,3 +98,42 @@ def test_sharded_test_tile_matches_oracle_test_tile():
         want = O.test_tile(sd, x, 4, 16, 8)
         got = sharded_test_tile(lambda t: O.test(sd, t, 4), x, 4, 16, 8, rank=0, world=1)
     assert (got - want).abs().max().item() <= 1e-5
+
+
+def _peer_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from femasr_b200.parallel import PeerGather
+        shape = (3, 3, 16, 24)
+        pg = PeerGather(shape, torch.float32, dev, rank, world, nbuf=2)          # includes the collective self-check
+        ok = True
+        for k in (0, 1, 0):
+            shard = torch.full(shape, float(10 * k + rank + 1), device=dev)
+            pg.push(k, shard).synchronize()
+            dist.barrier()
+            want = torch.cat([torch.full(shape, float(10 * k + r + 1)) for r in range(world)], 0)
+            ok = ok and torch.equal(pg.full[k].cpu(), want)
+            dist.barrier()
+        pg.close()
+        dist.barrier()
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_world2_peer_gather_matches_all_gather():
+    """PeerGather (copy-engine peer writes over CUDA IPC) fills every rank's buffer like all_gather_into_tensor.  Needs
+    two GPUs with peer access; skipped on the single-GPU test box (bench.py --gpus 2 exercises the same path there)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ret = mp.Manager().dict()
+    mp.spawn(_peer_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
