@@ -129,8 +129,8 @@ def _peer_worker(rank, world, port, ret):
 def test_world2_peer_gather_matches_all_gather():
     """PeerGather (copy-engine peer writes over CUDA IPC) fills every rank's buffer like all_gather_into_tensor.  Needs
     two GPUs with peer access; skipped on the single-GPU test box (bench.py --gpus 2 exercises the same path there)."""
-    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2 or os.environ.get("FEMASR_TEST_MULTI_GPU") != "1":
+        pytest.skip("needs two GPUs and FEMASR_TEST_MULTI_GPU=1 (spawns two NCCL ranks)")
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
