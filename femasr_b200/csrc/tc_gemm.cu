@@ -555,7 +555,7 @@ tc_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         // fetch, not the math, occupies the pipe.  Input strip sr feeds tap row kh = sr - r of every output row r it
         // touches WITH THE SAME A operand, and the accumulators of rows r, r + 1, ... sit side by side in TMEM, so those
         // products are ONE MMA of N = 64 x rows against the weight rows of kh = sr - r_lo, ..., sr - r_hi (contiguous in
-        // the merged layout): 144 instead of 288 MMAs per 4-row work item, A fetched once per strip and k-step instead of
+        // the merged layout): 147 instead of 288 MMAs per 4-row work item, A fetched once per strip and k-step instead of
         // once per (row, tap).  Every accumulator still receives its contributions in (kh, kw, k, product) order, so the
         // results are bit-identical to the unmerged form.  Only the very first product into a fresh accumulator (kh = 0,
         // kw = 0, k = 0) must overwrite instead of accumulate and is issued on its own.
